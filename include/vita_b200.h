@@ -1,0 +1,161 @@
+/* libvita_b200.so -- C ABI of the B200-native (sm_100a) kernels behind VITA's omni-modal prefill + decode forward.
+ *
+ * The reference (VITA-MLLM/VITA) is pure Python and has no FFI of its own: every GPU op is reached through
+ * torch / transformers / flash-attn / vLLM wheels.  This header is therefore the boundary a maintainer binds with
+ * ctypes; each entry point names the reference call site (file:line under the reference tree)
+ * whose library kernel it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers unless stated otherwise;
+ *   - bf16 storage (uint16 payload), fp32 accumulation; row-major; weights are [out_features, in_features]
+ *     exactly as torch.nn.Linear stores them;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns VITA_OK (0) or a negative error code and records a message retrievable with
+ *     vita_last_error(); nothing allocates device memory (workspaces are passed in);
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU the launches fail with VITA_ERR_CUDA.
+ */
+#ifndef VITA_B200_H
+#define VITA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITA_OK 0
+#define VITA_ERR_INVALID (-1)
+#define VITA_ERR_CUDA (-2)
+
+#define VITA_ACT_NONE 0
+#define VITA_ACT_GELU 1 /* erf GELU (torch.nn.GELU default) */
+#define VITA_ACT_RELU 2
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+int vita_version(void);
+const char* vita_last_error(void);
+/* number of SMs of the current device (0 if no CUDA device is usable) */
+int vita_num_sms(void);
+/* counts kernels launched through this library since the last reset (bench.py's gpu_launches) */
+int64_t vita_launch_count(int reset);
+
+/* ---- dense linear:  C[M,N] = residual + colscale * act(A[M,K] . B[N,K]^T + bias) ----------------------------
+ * tcgen05 / TMEM / TMA GEMM.  Replaces nn.Linear -> cuBLAS at
+ *   internvit/modeling_intern_vit.py:180 (qkv), :192 (proj, with ls1 + residual :245-247),
+ *   :214,216 (fc1+GELU, fc2 with ls2 + residual :249-251); multimodal_projector/builder.py:164-168;
+ *   whale/module/layer/attention.py:371-373,381,419; :145-147; component/subsampling.py:34;
+ *   component/transformer.py:313; adapter.py:94,104; transformers MixtralAttention q/k/v/o_proj;
+ *   lm_head on all rows (vita_mixtral.py:171-173).
+ * bias [N] / colscale [N] / residual [M, ldr] may be NULL.  K, lda, ldc, ldr multiples of 8; 16-byte aligned. */
+int vita_gemm_bf16(const void* A, int64_t lda, const void* B, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                   const void* bias, int act, const void* colscale, const void* residual, int64_t ldr, void* stream);
+
+/* ---- row kernels ------------------------------------------------------------------------------------------ */
+/* transformers MixtralRMSNorm.forward (modeling_mixtral.py:148-153). */
+int vita_rmsnorm(const void* x, const void* w, void* y, int64_t rows, int64_t H, float eps, void* stream);
+/* torch.nn.LayerNorm + optional activation + output scale: modeling_intern_vit.py:229-230;
+ * whale transformer.py:88-89,313-318 (LayerNorm -> ReLU, then x sqrt(d) attention.py:109),:371; adapter.py:98-104. */
+int vita_layernorm(const void* x, const void* w, const void* b, void* y, int64_t rows, int64_t H, float eps, int act,
+                   float out_scale, void* stream);
+/* out[dst_index[i]] = table[src_index[i]] (NULL index = identity, negative = skip): embed_tokens
+ * (vita_arch.py:274), placeholder splice (vita_arch.py:277-303; mixtral.py:1116,1126), MoE token gather. */
+int vita_row_copy(const void* table, const int32_t* src_index, const int32_t* dst_index, void* out, int64_t n_rows,
+                  int64_t H, void* stream);
+/* rotate-half RoPE on the q and k heads of a fused qkv activation, in place, and append k/v to the paged cache
+ * (modeling_mixtral.py:224-254; vLLM twin mixtral.py:477-501).  cos_sin fp32 [max_pos, 2, D/2]; slot_mapping[tok] =
+ * page * page_size + offset (NULL = do not write the cache). */
+int vita_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_mapping, const float* cos_sin,
+                       void* k_cache, void* v_cache, int64_t n_tok, int64_t n_q_heads, int64_t n_kv_heads,
+                       int64_t head_dim, void* stream);
+
+/* ---- attention -------------------------------------------------------------------------------------------- */
+/* softmax(Q K^T * scale [causal] [kv_lens mask]) V, FlashAttention style.  Strides are {batch, token, head} in
+ * elements.  Supported (d_qk, d_v): (128,128) Mixtral GQA, (64,64) InternViT, (128,64) Whale rel-pos with the
+ * operands prepared by vita_whale_qk_prep.  Replaces flash_attn_varlen_qkvpacked_func
+ * (internvit/flash_attention.py:61), whale attention.py:391-415, transformers sdpa (modeling_mixtral.py:269-292). */
+int vita_attention_fwd(const void* q, const void* k, const void* v, void* o, const int64_t* q_strides,
+                       const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides, int64_t B,
+                       int64_t n_q_heads, int64_t n_kv_heads, int64_t Sq, int64_t Skv, int64_t d_qk, int64_t d_v,
+                       const int32_t* kv_lens, int causal, float scale, void* stream);
+/* single-query paged-KV attention for decode (vLLM paged Attention, mixtral.py:484-501).  workspace must be
+ * zero-initialised once and be at least vita_decode_attention_workspace_bytes() large. */
+int64_t vita_decode_attention_workspace_bytes(int64_t B, int64_t n_kv_heads, int64_t splits);
+int vita_decode_attention(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table,
+                          const int32_t* cur_pos, void* out, void* workspace, int64_t B, int64_t n_q_heads,
+                          int64_t n_kv_heads, int64_t head_dim, int64_t page_size, int64_t max_pages, int64_t splits,
+                          float scale, void* stream);
+
+/* ---- sparse MoE (prefill) --------------------------------------------------------------------------------- */
+/* post_attention_layernorm + MixtralTopKRouter (modeling_mixtral.py:109-116; vLLM FusedMoE renormalize=True,
+ * mixtral.py:405-414): writes the normed activations xn, top-2 expert ids and renormalised weights. */
+int vita_moe_router(const void* h, const void* norm_w, const void* gate_w, void* xn, int32_t* topk_ids, float* topk_w,
+                    int64_t n_tok, int64_t H, int64_t E, float eps, void* stream);
+/* stable counting sort of the (token, k) assignments by expert: expert_offsets [E+1], perm_row [n_tok*2],
+ * row_token [n_tok*2], row_weight [n_tok*2] (replaces the one_hot / torch.where bookkeeping, modeling_mixtral.py:81-90). */
+int vita_moe_align(const int32_t* topk_ids, const float* topk_w, int32_t* expert_offsets, int32_t* perm_row,
+                   int32_t* row_token, float* row_weight, int64_t n_tok, int64_t E, void* stream);
+/* grouped expert GEMMs over the permuted rows (modeling_mixtral.py:91-95):
+ *   Act[r, :]    = silu(X[r] . Wg_e^T) * (X[r] . Wu_e^T)   with W_gate_up [E, 2I, H] (gate rows first)
+ *   Y_perm[r, :] = row_weight[r] * (Act[r] . Wd_e^T)       with W_down [E, H, I] */
+int vita_moe_gemm_gate_up_silu(const void* X_perm, const void* W_gate_up, void* Act, const int32_t* expert_offsets,
+                               int64_t rows, int64_t num_experts, int64_t H, int64_t I, void* stream);
+int vita_moe_gemm_down(const void* Act, const void* W_down, void* Y_perm, const int32_t* expert_offsets,
+                       const float* row_weight, int64_t rows, int64_t num_experts, int64_t H, int64_t I, void* stream);
+/* h[t] += Y_perm[perm_row[t,0]] + Y_perm[perm_row[t,1]] (index_add_ + residual, modeling_mixtral.py:96,386-389);
+ * if next_norm_w != NULL also writes xn_out = RMSNorm(h) for the next layer / final norm. */
+int vita_moe_combine(void* h, const void* y_perm, const int32_t* perm_row, const void* next_norm_w, void* xn_out,
+                     int64_t n_tok, int64_t H, float eps, void* stream);
+
+/* ---- InternViT front / back end --------------------------------------------------------------------------- */
+/* im2col for Conv2d(3,1024,k=14,s=14) (modeling_intern_vit.py:80-85,109): out [n_img*(HW/P)^2, k_pad]. */
+int vita_vit_im2col(const void* images, void* out, int64_t n_img, int64_t C, int64_t HW, int64_t P, int64_t k_pad,
+                    void* stream);
+/* cat([cls, patches]) + position_embedding (modeling_intern_vit.py:112-121). */
+int vita_vit_assemble(const void* patches, const void* cls, const void* pos, void* out, int64_t n_img, int64_t n_patch,
+                      int64_t H, void* stream);
+/* drop CLS, x scale, pixel_shuffle(0.5) (internvit_encoder.py:35-53,71-77): [n,1+g*g,C] -> [n,(g/2)^2,4C]. */
+int vita_vit_pixel_shuffle(const void* h, void* out, int64_t n_img, int64_t grid, int64_t C, float scale,
+                           void* stream);
+
+/* ---- Whale audio front end -------------------------------------------------------------------------------- */
+/* GlobalCMVN (cmvn.py:21-32, mean/istd may be NULL) + Conv2d(1,C,3,2) + ReLU (subsampling.py:28-29); feat fp32
+ * [B,T,F]; out channels-last [B,T1,F1,C]. */
+int vita_whale_conv1(const float* feat, const float* mean, const float* istd, const void* w, const void* bias,
+                     void* out, int64_t B, int64_t T, int64_t F, int64_t C, void* stream);
+/* im2col for Conv2d(C,C,3,2) on the channels-last map (subsampling.py:30): out [B*T2*F2, 9*C]. */
+int vita_whale_im2col2(const void* in, void* out, int64_t B, int64_t T1, int64_t F1, int64_t C, void* stream);
+/* rel-pos attention operands (attention.py:379-398): Q2 = [q+u | q+v], K2 = [k | p], each [B*T, heads, 2*dk]. */
+int vita_whale_qk_prep(const void* qkv, const void* p, const void* bias_u, const void* bias_v, void* q2, void* k2,
+                       int64_t B, int64_t T, int64_t heads, int64_t dk, void* stream);
+/* adapter front (adapter.py:112-121): mask padded frames, right-pad k-1, im2col for Conv1d(C,2C,k,stride 2). */
+int vita_whale_adapter_im2col(const void* x, const int32_t* lengths, void* out, int64_t B, int64_t T, int64_t C,
+                              int64_t ksize, void* stream);
+
+/* ---- greedy decode step (weight-streaming GEMVs) ---------------------------------------------------------- */
+/* consume the previous arg-max (best[b]), append it to token_log, advance cache_len, gather its embedding. */
+int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* gen_count, int64_t max_log, int32_t* cache_len,
+                      int32_t* cur_pos, const void* embed, void* h, int64_t B, int64_t H, int64_t vocab, void* stream);
+/* input_layernorm + fused q/k/v projection + RoPE + paged-KV append for one token per sequence. */
+int vita_decode_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, const float* cos_sin,
+                         const int32_t* cur_pos, const int32_t* block_table, void* q_out, void* k_cache, void* v_cache,
+                         int64_t B, int64_t H, int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim,
+                         int64_t page_size, int64_t max_pages, float eps, void* stream);
+/* h += x . W^T (o_proj + residual). */
+int vita_decode_oproj(const void* x, const void* w, void* h, int64_t B, int64_t N, int64_t K, void* stream);
+/* post_attention_layernorm + router (top-2 of 8). */
+int vita_decode_router(const void* h, const void* norm_w, const void* gate_w, void* xn, int32_t* topk_ids,
+                       float* topk_w, int64_t B, int64_t H, int64_t E, float eps, void* stream);
+/* the two selected experts: act[b,k,:] = silu(gate) * up ; h[b] += sum_k w_k * down_k(act[b,k]). */
+int vita_decode_moe_gate_up(const void* xn, const void* w13, const int32_t* topk_ids, void* act, int64_t B, int64_t H,
+                            int64_t I, void* stream);
+int vita_decode_moe_down(const void* act, const void* w2, const int32_t* topk_ids, const float* topk_w, void* h,
+                         int64_t B, int64_t H, int64_t I, void* stream);
+/* final RMSNorm + lm_head on one row per sequence + arg-max on the bf16 logits (vita_mixtral.py:171-173 and the
+ * greedy step of HF generate(), video_audio_demo.py:257-270).  logits may be NULL; best[b] must be 0 on entry. */
+int vita_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
+                        uint64_t* best, int64_t B, int64_t H, int64_t V, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITA_B200_H */

@@ -1,0 +1,467 @@
+// Attention kernels.
+//
+// (1) flash_fwd_kernel<DQK, DV>: FlashAttention-style fused softmax(Q K^T * scale) V for the three prefill-shaped
+//     attentions of the path: Mixtral causal GQA (128/128), InternViT non-causal (64/64), Whale rel-pos with the two
+//     score terms folded into one contraction over [k | p] (128/64).  K/V tiles are staged through XOR-swizzled shared
+//     memory with cp.async double buffering; the contractions run on mma.sync m16n8k16 bf16 (legacy tensor path --
+//     attention is < 1% of the prefill FLOPs at the BASELINE sequence lengths; the tcgen05 port is DESIGN.md "next").
+// (2) decode_attn_kernel: single-query paged-KV attention for greedy decode.  One CTA per (kv head, context split);
+//     the 4 query heads of a GQA group share every K/V load; 8-lane groups own one key each and reduce with warp
+//     shuffles; splits are merged by the last CTA to finish (self-resetting ticket).
+//
+// Reference call sites: flash_attn_varlen_qkvpacked_func (internvit/flash_attention.py:61) / naive softmax
+// (modeling_intern_vit.py:170-174); whale attention.py:391-415; transformers sdpa/eager attention
+// (modeling_mixtral.py:269-292); vLLM paged Attention (web_demo/vllm_tools/vllm_file/mixtral.py:484-501).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vita {
+
+struct AttnParams {
+    const __nv_bfloat16* q;
+    const __nv_bfloat16* k;
+    const __nv_bfloat16* v;
+    __nv_bfloat16* o;
+    long long q_bs, q_ts, q_hs;  // batch / token / head strides in elements
+    long long k_bs, k_ts, k_hs;
+    long long v_bs, v_ts, v_hs;
+    long long o_bs, o_ts, o_hs;
+    int group;         // query heads per kv head
+    int Sq, Skv;
+    const int* kv_lens;  // [B] valid keys per batch entry, or nullptr
+    int causal;
+    float scale_log2;  // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// byte offset of 16-byte chunk `chunk` of row `row` in a [rows][D] bf16 tile with XOR swizzle
+template <int D>
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+    return static_cast<uint32_t>(row * D * 2 + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int D>
+__device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_bfloat16* g, long long tok_stride,
+                                                int row0, int n_valid_rows) {
+    constexpr int CPR = D / 8;  // chunks per row
+    constexpr int TOTAL = 64 * CPR;
+#pragma unroll
+    for (int i = 0; i < TOTAL / 128; ++i) {
+        const int c = threadIdx.x + i * 128;
+        const int r = c / CPR, ch = c % CPR;
+        const bool ok = (row0 + r) < n_valid_rows;
+        const __nv_bfloat16* src = g + static_cast<long long>(ok ? (row0 + r) : 0) * tok_stride + ch * 8;
+        cp_async16(smem_base + swz<D>(r, ch), src, ok);
+    }
+}
+
+template <int DQK, int DV>
+__global__ void __launch_bounds__(128)
+flash_fwd_kernel(const AttnParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sQ = smem_u32(smem);
+    const uint32_t sK = sQ + 64 * DQK * 2;
+    const uint32_t sV = sK + 2 * 64 * DQK * 2;
+
+    const int m_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int kvh = head / p.group;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int kv_len = p.kv_lens ? p.kv_lens[b] : p.Skv;
+    if (kv_len > p.Skv) kv_len = p.Skv;
+    const int q0 = m_blk * 64;
+    int n_tiles = (kv_len + 63) / 64;
+    if (p.causal && n_tiles > m_blk + 1) n_tiles = m_blk + 1;
+
+    const __nv_bfloat16* qg = p.q + b * p.q_bs + head * p.q_hs;
+    const __nv_bfloat16* kg = p.k + b * p.k_bs + kvh * p.k_hs;
+    const __nv_bfloat16* vg = p.v + b * p.v_bs + kvh * p.v_hs;
+
+    load_tile_async<DQK>(sQ, qg, p.q_ts, q0, p.Sq);
+    if (n_tiles > 0) {
+        load_tile_async<DQK>(sK, kg, p.k_ts, 0, kv_len);
+        load_tile_async<DV>(sV, vg, p.v_ts, 0, kv_len);
+    }
+    cp_async_commit();
+
+    float o_acc[DV / 8][4];
+#pragma unroll
+    for (int i = 0; i < DV / 8; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o_acc[i][e] = 0.0f;
+    float m_i[2] = {-INFINITY, -INFINITY};
+    float l_i[2] = {0.0f, 0.0f};
+    uint32_t q_frag[DQK / 16][4];
+
+    const int g = lane >> 2, tq = lane & 3;
+    const int ld_i = lane >> 3, ld_r = lane & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+        const int buf = j & 1;
+        if (j + 1 < n_tiles) {
+            load_tile_async<DQK>(sK + (buf ^ 1) * 64 * DQK * 2, kg, p.k_ts, (j + 1) * 64, kv_len);
+            load_tile_async<DV>(sV + (buf ^ 1) * 64 * DV * 2, vg, p.v_ts, (j + 1) * 64, kv_len);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (j == 0) {
+#pragma unroll
+            for (int ks = 0; ks < DQK / 16; ++ks)
+                ldsm_x4(sQ + swz<DQK>(warp * 16 + (ld_i & 1) * 8 + ld_r, ks * 2 + (ld_i >> 1)), q_frag[ks][0],
+                        q_frag[ks][1], q_frag[ks][2], q_frag[ks][3]);
+        }
+        const uint32_t kb = sK + buf * 64 * DQK * 2;
+        const uint32_t vb = sV + buf * 64 * DV * 2;
+
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[i][e] = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < DQK / 16; ++ks) {
+#pragma unroll
+            for (int nt2 = 0; nt2 < 4; ++nt2) {
+                uint32_t r0, r1, r2, r3;
+                ldsm_x4(kb + swz<DQK>(nt2 * 16 + (ld_i >> 1) * 8 + ld_r, ks * 2 + (ld_i & 1)), r0, r1, r2, r3);
+                mma16816(s[nt2 * 2], q_frag[ks], r0, r1);
+                mma16816(s[nt2 * 2 + 1], q_frag[ks], r2, r3);
+            }
+        }
+
+        // scale, mask, online softmax (base 2)
+        const int row_lo = q0 + warp * 16 + g;
+        float rmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = j * 64 + nt * 8 + tq * 2 + (e & 1);
+                const int row = row_lo + (e >> 1) * 8;
+                float v = s[nt][e] * p.scale_log2;
+                if (col >= kv_len || (p.causal && col > row)) v = -INFINITY;
+                s[nt][e] = v;
+                rmax[e >> 1] = fmaxf(rmax[e >> 1], v);
+            }
+        }
+        float alpha[2], m_safe[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 1));
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 2));
+            const float m_new = fmaxf(m_i[r], rmax[r]);
+            m_safe[r] = (m_new == -INFINITY) ? 0.0f : m_new;
+            alpha[r] = exp2f(m_i[r] - m_safe[r]);
+            m_i[r] = m_new;
+        }
+        float rsum[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float pv = exp2f(s[nt][e] - m_safe[e >> 1]);
+                s[nt][e] = pv;
+                rsum[e >> 1] += pv;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l_i[r] = l_i[r] * alpha[r] + rsum[r];
+#pragma unroll
+        for (int dt = 0; dt < DV / 8; ++dt) {
+            o_acc[dt][0] *= alpha[0];
+            o_acc[dt][1] *= alpha[0];
+            o_acc[dt][2] *= alpha[1];
+            o_acc[dt][3] *= alpha[1];
+        }
+        // O += P V
+#pragma unroll
+        for (int ks2 = 0; ks2 < 4; ++ks2) {
+            uint32_t a[4];
+            a[0] = pack_bf16(s[ks2 * 2][0], s[ks2 * 2][1]);
+            a[1] = pack_bf16(s[ks2 * 2][2], s[ks2 * 2][3]);
+            a[2] = pack_bf16(s[ks2 * 2 + 1][0], s[ks2 * 2 + 1][1]);
+            a[3] = pack_bf16(s[ks2 * 2 + 1][2], s[ks2 * 2 + 1][3]);
+#pragma unroll
+            for (int dt2 = 0; dt2 < DV / 16; ++dt2) {
+                uint32_t r0, r1, r2, r3;
+                ldsm_x4_t(vb + swz<DV>(ks2 * 16 + (ld_i & 1) * 8 + ld_r, dt2 * 2 + (ld_i >> 1)), r0, r1, r2, r3);
+                mma16816(o_acc[dt2 * 2], a, r0, r1);
+                mma16816(o_acc[dt2 * 2 + 1], a, r2, r3);
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+    }
+    __nv_bfloat16* og = p.o + b * p.o_bs + head * p.o_hs;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + g + r * 8;
+        if (row >= p.Sq) continue;
+        const float inv = l_i[r] > 0.0f ? 1.0f / l_i[r] : 0.0f;
+        __nv_bfloat16* orow = og + static_cast<long long>(row) * p.o_ts;
+#pragma unroll
+        for (int dt = 0; dt < DV / 8; ++dt) {
+            const uint32_t packed = pack_bf16(o_acc[dt][r * 2] * inv, o_acc[dt][r * 2 + 1] * inv);
+            *reinterpret_cast<uint32_t*>(orow + dt * 8 + tq * 2) = packed;
+        }
+    }
+}
+
+template <int DQK, int DV>
+static int launch_flash(const AttnParams& p, int B, int Hq, cudaStream_t st) {
+    constexpr int smem_bytes = 64 * DQK * 2 + 2 * 64 * DQK * 2 + 2 * 64 * DV * 2;
+    static bool configured = false;
+    auto kern = flash_fwd_kernel<DQK, DV>;
+    if (!configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
+                            "cudaFuncSetAttribute(flash smem)");
+        if (rc) return rc;
+        configured = true;
+    }
+    dim3 grid((p.Sq + 63) / 64, Hq, B);
+    kern<<<grid, 128, smem_bytes, st>>>(p);
+    return check_launch("flash_fwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ paged decode
+constexpr int DEC_D = 128;     // head dim
+constexpr int DEC_GROUP = 4;   // query heads per kv head (32 / 8)
+
+struct DecodeAttnParams {
+    const __nv_bfloat16* q;        // [B, n_q, D]
+    const __nv_bfloat16* k_cache;  // [slots, n_kv, D]
+    const __nv_bfloat16* v_cache;
+    const int* block_table;        // [B, max_pages]
+    const int* cur_pos;            // [B] position of the current token; context = cur_pos + 1
+    __nv_bfloat16* out;            // [B, n_q * D]
+    float* part_o;                 // [B, n_kv, splits, GROUP, D]
+    float* part_ml;                // [B, n_kv, splits, GROUP, 2]
+    int* tickets;                  // [B, n_kv], zero-initialised, self-resetting
+    int n_q, n_kv, page_size, max_pages, splits;
+    float scale_log2;
+};
+
+__global__ void __launch_bounds__(128)
+decode_attn_kernel(const DecodeAttnParams p) {
+    __shared__ float s_m[16][DEC_GROUP];
+    __shared__ float s_l[16][DEC_GROUP];
+    __shared__ float s_o[16][DEC_GROUP][DEC_D];
+    __shared__ int s_last;
+
+    const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+    const int ctx = p.cur_pos[b] + 1;
+    const int per = (ctx + p.splits - 1) / p.splits;
+    const int k_begin = split * per;
+    const int k_end = min(ctx, k_begin + per);
+
+    const int lg = threadIdx.x >> 3;  // lane group 0..15: one key at a time
+    const int sl = threadIdx.x & 7;   // 16 dims per lane
+    const int d0 = sl * 16;
+
+    float q[DEC_GROUP][16];
+#pragma unroll
+    for (int h = 0; h < DEC_GROUP; ++h) {
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q + (static_cast<long long>(b) * p.n_q + kvh * DEC_GROUP + h) * DEC_D + d0);
+        const uint4 a = qp[0], c = qp[1];
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { q[h][2 * i] = bf16_lo(w[i]); q[h][2 * i + 1] = bf16_hi(w[i]); }
+    }
+    float m[DEC_GROUP], l[DEC_GROUP], acc[DEC_GROUP][16];
+#pragma unroll
+    for (int h = 0; h < DEC_GROUP; ++h) {
+        m[h] = -INFINITY;
+        l[h] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[h][i] = 0.0f;
+    }
+    const int* bt = p.block_table + static_cast<long long>(b) * p.max_pages;
+    for (int key0 = k_begin; key0 < k_end; key0 += 16) {  // trip count is uniform across the warp (shuffles below)
+        const int key = key0 + lg;
+        const bool valid = key < k_end;
+        float kf[16], vf[16];
+        if (valid) {
+            const int page = bt[key / p.page_size];
+            const long long slot = static_cast<long long>(page) * p.page_size + key % p.page_size;
+            const uint4* kp = reinterpret_cast<const uint4*>(p.k_cache + (slot * p.n_kv + kvh) * DEC_D + d0);
+            const uint4* vp = reinterpret_cast<const uint4*>(p.v_cache + (slot * p.n_kv + kvh) * DEC_D + d0);
+            const uint4 ka = kp[0], kc = kp[1], va = vp[0], vc = vp[1];
+            const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kc.x, kc.y, kc.z, kc.w};
+            const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                kf[2 * i] = bf16_lo(kw[i]); kf[2 * i + 1] = bf16_hi(kw[i]);
+                vf[2 * i] = bf16_lo(vw[i]); vf[2 * i + 1] = bf16_hi(vw[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { kf[i] = 0.0f; vf[i] = 0.0f; }
+        }
+#pragma unroll
+        for (int h = 0; h < DEC_GROUP; ++h) {
+            float dot = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dot += q[h][i] * kf[i];
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            if (valid) {
+                const float sc = dot * p.scale_log2;
+                const float m_new = fmaxf(m[h], sc);
+                const float alpha = exp2f(m[h] - m_new);
+                const float pr = exp2f(sc - m_new);
+                m[h] = m_new;
+                l[h] = l[h] * alpha + pr;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[h][i] = acc[h][i] * alpha + pr * vf[i];
+            }
+        }
+    }
+    // merge the 16 lane groups of this CTA
+#pragma unroll
+    for (int h = 0; h < DEC_GROUP; ++h) {
+        if (sl == 0) { s_m[lg][h] = m[h]; s_l[lg][h] = l[h]; }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s_o[lg][h][d0 + i] = acc[h][i];
+    }
+    __syncthreads();
+    const int d = threadIdx.x;  // one output dim per thread
+    const long long pbase = ((static_cast<long long>(b) * p.n_kv + kvh) * p.splits + split) * DEC_GROUP;
+#pragma unroll
+    for (int h = 0; h < DEC_GROUP; ++h) {
+        float mm = -INFINITY;
+#pragma unroll
+        for (int gI = 0; gI < 16; ++gI) mm = fmaxf(mm, s_m[gI][h]);
+        float ll = 0.0f, oo = 0.0f;
+        if (mm > -INFINITY) {
+#pragma unroll
+            for (int gI = 0; gI < 16; ++gI) {
+                const float w = exp2f(s_m[gI][h] - mm);
+                ll += w * s_l[gI][h];
+                oo += w * s_o[gI][h][d];
+            }
+        }
+        p.part_o[(pbase + h) * DEC_D + d] = oo;
+        if (d == 0) { p.part_ml[(pbase + h) * 2] = mm; p.part_ml[(pbase + h) * 2 + 1] = ll; }
+    }
+    // last CTA of this (batch, kv head) merges the splits
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(&p.tickets[b * p.n_kv + kvh], 1);
+        s_last = (t == p.splits - 1);
+        if (s_last) p.tickets[b * p.n_kv + kvh] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const long long sbase = (static_cast<long long>(b) * p.n_kv + kvh) * p.splits * DEC_GROUP;
+#pragma unroll
+    for (int h = 0; h < DEC_GROUP; ++h) {
+        float mm = -INFINITY;
+        for (int s = 0; s < p.splits; ++s) mm = fmaxf(mm, __ldcg(&p.part_ml[(sbase + s * DEC_GROUP + h) * 2]));
+        float ll = 0.0f, oo = 0.0f;
+        for (int s = 0; s < p.splits; ++s) {
+            const float ms = __ldcg(&p.part_ml[(sbase + s * DEC_GROUP + h) * 2]);
+            if (ms == -INFINITY) continue;
+            const float w = exp2f(ms - mm);
+            ll += w * __ldcg(&p.part_ml[(sbase + s * DEC_GROUP + h) * 2 + 1]);
+            oo += w * __ldcg(&p.part_o[(sbase + s * DEC_GROUP + h) * DEC_D + d]);
+        }
+        p.out[(static_cast<long long>(b) * p.n_q + kvh * DEC_GROUP + h) * DEC_D + d] =
+            __float2bfloat16(ll > 0.0f ? oo / ll : 0.0f);
+    }
+}
+
+}  // namespace vita
+
+using namespace vita;
+
+extern "C" int vita_attention_fwd(const void* q, const void* k, const void* v, void* o, const int64_t* q_strides,
+                                  const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
+                                  int64_t B, int64_t n_q_heads, int64_t n_kv_heads, int64_t Sq, int64_t Skv,
+                                  int64_t d_qk, int64_t d_v, const int32_t* kv_lens, int causal, float scale,
+                                  void* stream) {
+    VITA_REQUIRE(n_kv_heads > 0 && n_q_heads % n_kv_heads == 0, "n_q_heads must be a multiple of n_kv_heads");
+    VITA_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "q/k/v/o must be 16-byte aligned");
+    for (int i = 0; i < 3; ++i)
+        VITA_REQUIRE(q_strides[i] % 8 == 0 && k_strides[i] % 8 == 0 && v_strides[i] % 8 == 0 && o_strides[i] % 2 == 0,
+                     "strides must keep 16-byte row alignment");
+    if (B == 0 || Sq == 0) return VITA_OK;
+    AttnParams p{};
+    p.q = BF16C(q); p.k = BF16C(k); p.v = BF16C(v); p.o = static_cast<__nv_bfloat16*>(o);
+    p.q_bs = q_strides[0]; p.q_ts = q_strides[1]; p.q_hs = q_strides[2];
+    p.k_bs = k_strides[0]; p.k_ts = k_strides[1]; p.k_hs = k_strides[2];
+    p.v_bs = v_strides[0]; p.v_ts = v_strides[1]; p.v_hs = v_strides[2];
+    p.o_bs = o_strides[0]; p.o_ts = o_strides[1]; p.o_hs = o_strides[2];
+    p.group = static_cast<int>(n_q_heads / n_kv_heads);
+    p.Sq = static_cast<int>(Sq);
+    p.Skv = static_cast<int>(Skv);
+    p.kv_lens = kv_lens;
+    p.causal = causal;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    auto st = static_cast<cudaStream_t>(stream);
+    if (d_qk == 128 && d_v == 128) return launch_flash<128, 128>(p, (int)B, (int)n_q_heads, st);
+    if (d_qk == 64 && d_v == 64) return launch_flash<64, 64>(p, (int)B, (int)n_q_heads, st);
+    if (d_qk == 128 && d_v == 64) return launch_flash<128, 64>(p, (int)B, (int)n_q_heads, st);
+    set_last_error("vita_attention_fwd: unsupported head dims (supported: 128/128, 64/64, 128/64)");
+    return VITA_ERR_INVALID;
+}
+
+extern "C" int64_t vita_decode_attention_workspace_bytes(int64_t B, int64_t n_kv_heads, int64_t splits) {
+    const int64_t n = B * n_kv_heads * splits * DEC_GROUP;
+    return n * DEC_D * 4 + n * 2 * 4 + B * n_kv_heads * 4 + 256;
+}
+
+extern "C" int vita_decode_attention(const void* q, const void* k_cache, const void* v_cache,
+                                     const int32_t* block_table, const int32_t* cur_pos, void* out, void* workspace,
+                                     int64_t B, int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim,
+                                     int64_t page_size, int64_t max_pages, int64_t splits, float scale, void* stream) {
+    VITA_REQUIRE(head_dim == DEC_D && n_q_heads == n_kv_heads * DEC_GROUP, "decode attention: need D=128, GQA group 4");
+    VITA_REQUIRE(splits >= 1 && workspace != nullptr, "splits >= 1 and a workspace are required");
+    if (B == 0) return VITA_OK;
+    DecodeAttnParams p{};
+    p.q = BF16C(q); p.k_cache = BF16C(k_cache); p.v_cache = BF16C(v_cache);
+    p.block_table = block_table; p.cur_pos = cur_pos; p.out = static_cast<__nv_bfloat16*>(out);
+    const int64_t n = B * n_kv_heads * splits * DEC_GROUP;
+    // tickets first (must be zero-initialised once by the caller; the kernel resets them)
+    p.tickets = static_cast<int*>(workspace);
+    char* w = static_cast<char*>(workspace) + ((B * n_kv_heads * 4 + 255) / 256) * 256;
+    p.part_o = reinterpret_cast<float*>(w);
+    p.part_ml = reinterpret_cast<float*>(w + n * DEC_D * 4);
+    p.n_q = (int)n_q_heads; p.n_kv = (int)n_kv_heads; p.page_size = (int)page_size; p.max_pages = (int)max_pages;
+    p.splits = (int)splits;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    dim3 grid((unsigned)splits, (unsigned)n_kv_heads, (unsigned)B);
+    decode_attn_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("decode_attn_kernel");
+}

@@ -1,0 +1,39 @@
+// Host-side helpers shared by all translation units of libvita_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/vita_b200.h"
+
+namespace vita {
+
+void set_last_error(const std::string& msg);
+int num_sms();
+
+// Returns VITA_OK or records the CUDA error text and returns VITA_ERR_CUDA.
+int check_cuda(cudaError_t e, const char* what);
+int check_launch(const char* what);
+
+#define VITA_REQUIRE(cond, msg)                                                   \
+    do {                                                                          \
+        if (!(cond)) {                                                            \
+            ::vita::set_last_error(std::string(__func__) + ": " + (msg));         \
+            return VITA_ERR_INVALID;                                              \
+        }                                                                         \
+    } while (0)
+
+#define BF16C(p) static_cast<const __nv_bfloat16*>(p)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency).
+// dims/strides innermost-first; strides in bytes for dims 1..rank-1.
+int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                         const uint32_t* box, bool swizzle128);
+
+}  // namespace vita

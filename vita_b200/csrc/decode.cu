@@ -1,0 +1,502 @@
+// Greedy-decode step kernels (one new token per sequence): weight-streaming GEMVs, HBM-bound.
+//
+// Every linear of the decode step is a matrix-vector product whose cost is reading the weight once (25.2 GB per
+// token for Mixtral-8x7B).  All of them run on one skeleton, stream_gemv_kernel<Op>:
+//   * one CTA per SM, each owning a contiguous, balanced range of work items (an item = two weight rows);
+//   * warp 8 is a producer: one thread issues cp.async.bulk (TMA 1-D) copies of the item's rows into an 8-stage,
+//     16 KB/stage shared-memory ring with mbarrier complete_tx, so ~128 KB per SM is always in flight no matter what
+//     the consumers are doing;
+//   * warps 0-7 are consumers: conflict-free 16-byte LDS of weights and of the activation vector (bf16 in smem),
+//     fp32 FMA, warp-shuffle + one named barrier per item, then a fused per-item epilogue (RoPE + paged-KV write,
+//     residual add, SiLU*up, routing-weighted combine, bf16 logits + packed atomic arg-max).
+// Ops: QKV (input RMSNorm fused), O-proj (+residual), router (separate tiny kernel), expert gate/up (2 selected
+// experts), expert down (+weighted combine +residual), LM head (+final RMSNorm, +argmax).
+//
+// Reference: the decode step of HF generate() over transformers MixtralDecoderLayer (vita_mixtral.py:158-173,
+// video_audio_demo.py:257-270); vLLM twin web_demo/vllm_tools/vllm_file/mixtral.py:491-566.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vita {
+
+constexpr int GV_KC = 4096;                    // elements per row per stage
+constexpr int GV_STAGE_BYTES = 2 * GV_KC * 2;  // two rows of bf16
+constexpr int GV_STAGES = 8;
+constexpr int GV_CONSUMERS = 256;
+constexpr int GV_THREADS = GV_CONSUMERS + 32;
+
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float consumer_block_sum(float v, float* red8) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red8[threadIdx.x >> 5] = v;
+    consumer_barrier();
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red8[i];
+    consumer_barrier();
+    return t;
+}
+
+// xs[0..K) = bf16(rmsnorm(h) * w)   (consumer threads only)
+__device__ __forceinline__ void load_x_rmsnorm(const __nv_bfloat16* h, const __nv_bfloat16* w, __nv_bfloat16* xs, int K,
+                                               float eps, float* red8) {
+    float ss = 0.0f;
+    for (int i = threadIdx.x; i < K; i += GV_CONSUMERS) {
+        const float v = __bfloat162float(h[i]);
+        ss += v * v;
+    }
+    const float tot = consumer_block_sum(ss, red8);
+    const float inv = rsqrtf(tot / static_cast<float>(K) + eps);
+    for (int i = threadIdx.x; i < K; i += GV_CONSUMERS)
+        xs[i] = __float2bfloat16(__bfloat162float(h[i]) * inv * __bfloat162float(w[i]));
+}
+__device__ __forceinline__ void load_x_copy(const __nv_bfloat16* src, __nv_bfloat16* xs, int n) {
+    for (int i = threadIdx.x * 8; i < n; i += GV_CONSUMERS * 8)
+        *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(src + i);
+}
+
+struct FinishState {
+    float best;
+    int best_idx;
+};
+
+template <class Op>
+__global__ void __launch_bounds__(GV_THREADS, 1)
+stream_gemv_kernel(const Op op) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ring + GV_STAGES * GV_STAGE_BYTES);
+    uint8_t* tail = reinterpret_cast<uint8_t*>(xs) + ((op.x_elems() * 2 + 127) / 128) * 128;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + GV_STAGES;
+    float* red = reinterpret_cast<float*>(empty_bar + GV_STAGES);  // [2][8][2] + [8] scratch
+    float* red8 = red + 32;
+
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = op.K;
+    const int n_chunks = (K + GV_KC - 1) / GV_KC;
+    const long long n_items = op.num_items();
+    const int i0 = static_cast<int>(n_items * blockIdx.x / gridDim.x);
+    const int i1 = static_cast<int>(n_items * (blockIdx.x + 1) / gridDim.x);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GV_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 8);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = i0; item < i1; ++item) {
+                const __nv_bfloat16* r0 = op.row_ptr(b, item, 0);
+                const __nv_bfloat16* r1 = op.row_ptr(b, item, 1);
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int len = min(GV_KC, K - c * GV_KC);
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 11);
+                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(len) * 4);
+                    uint8_t* dst = ring + stage * GV_STAGE_BYTES;
+                    bulk_copy_g2s(dst, r0 + c * GV_KC, static_cast<uint32_t>(len) * 2, &full_bar[stage]);
+                    bulk_copy_g2s(dst + GV_KC * 2, r1 + c * GV_KC, static_cast<uint32_t>(len) * 2, &full_bar[stage]);
+                    if (++stage == GV_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers (256 threads)
+    op.load_x(b, xs, red8);
+    consumer_barrier();
+    FinishState st{-INFINITY, 0x7fffffff};
+    int stage = 0;
+    uint32_t phase = 0;
+    const int x1_off = op.x_per_row() ? K : 0;
+    for (int item = i0; item < i1; ++item) {
+        float a0 = 0.0f, a1 = 0.0f;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int len = min(GV_KC, K - c * GV_KC);
+            mbar_wait(&full_bar[stage], phase, 12);
+            const uint8_t* w0p = ring + stage * GV_STAGE_BYTES;
+            const uint8_t* w1p = w0p + GV_KC * 2;
+#pragma unroll
+            for (int pss = 0; pss < 2; ++pss) {
+                const int off = warp * 512 + pss * 256 + lane * 8;
+                if (off < len) {
+                    const uint4 w0 = *reinterpret_cast<const uint4*>(w0p + off * 2);
+                    const uint4 w1 = *reinterpret_cast<const uint4*>(w1p + off * 2);
+                    const uint4 x0 = *reinterpret_cast<const uint4*>(xs + c * GV_KC + off);
+                    const uint4 x1 = *reinterpret_cast<const uint4*>(xs + x1_off + c * GV_KC + off);
+                    const uint32_t a[4] = {w0.x, w0.y, w0.z, w0.w}, bb[4] = {w1.x, w1.y, w1.z, w1.w};
+                    const uint32_t xa[4] = {x0.x, x0.y, x0.z, x0.w}, xb[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a0 += bf16_lo(a[e]) * bf16_lo(xa[e]) + bf16_hi(a[e]) * bf16_hi(xa[e]);
+                        a1 += bf16_lo(bb[e]) * bf16_lo(xb[e]) + bf16_hi(bb[e]) * bf16_hi(xb[e]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == GV_STAGES) { stage = 0; phase ^= 1; }
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        float* rb = red + (item & 1) * 16;
+        if (lane == 0) { rb[warp * 2] = a0; rb[warp * 2 + 1] = a1; }
+        consumer_barrier();
+        if (warp == (item & 7) && lane == 0) {
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { s0 += rb[w * 2]; s1 += rb[w * 2 + 1]; }
+            op.finish(b, item, s0, s1, st);
+        }
+    }
+    op.finalize(b, st, red8);
+}
+
+// ------------------------------------------------------------------------------------------------ ops
+struct QkvOp {
+    const __nv_bfloat16* h;       // [B, H]
+    const __nv_bfloat16* norm_w;  // [H]
+    const __nv_bfloat16* w_qkv;   // [(n_q + 2 n_kv) * 128, H]
+    const float* cos_sin;         // [max_pos, 2, 64]
+    const int* cur_pos;           // [B]
+    const int* block_table;       // [B, max_pages]
+    __nv_bfloat16* q_out;         // [B, n_q * 128]
+    __nv_bfloat16* k_cache;       // [slots, n_kv, 128]
+    __nv_bfloat16* v_cache;
+    int K, n_q, n_kv, page_size, max_pages;
+    float eps;
+
+    __device__ int x_elems() const { return K; }
+    __device__ bool x_per_row() const { return false; }
+    __device__ long long num_items() const { return static_cast<long long>(n_q + 2 * n_kv) * 64; }
+    __device__ const __nv_bfloat16* row_ptr(int, int item, int r) const {
+        const int head = item >> 6, j = item & 63;
+        return w_qkv + static_cast<long long>(head * 128 + j + r * 64) * K;
+    }
+    __device__ void load_x(int b, __nv_bfloat16* xs, float* red8) const {
+        load_x_rmsnorm(h + static_cast<long long>(b) * K, norm_w, xs, K, eps, red8);
+    }
+    __device__ void finish(int b, int item, float s0, float s1, FinishState&) const {
+        const int head = item >> 6, j = item & 63;
+        const int pos = cur_pos[b];
+        // qkv projections are rounded to bf16 before RoPE, as the GEMM path (and the reference) does
+        s0 = __bfloat162float(__float2bfloat16(s0));
+        s1 = __bfloat162float(__float2bfloat16(s1));
+        if (head < n_q + n_kv) {
+            const float c = cos_sin[static_cast<long long>(pos) * 128 + j];
+            const float s = cos_sin[static_cast<long long>(pos) * 128 + 64 + j];
+            const float o0 = s0 * c - s1 * s, o1 = s1 * c + s0 * s;
+            s0 = o0;
+            s1 = o1;
+        }
+        if (head < n_q) {
+            __nv_bfloat16* q = q_out + (static_cast<long long>(b) * n_q + head) * 128;
+            q[j] = __float2bfloat16(s0);
+            q[j + 64] = __float2bfloat16(s1);
+        } else {
+            const int page = block_table[static_cast<long long>(b) * max_pages + pos / page_size];
+            const long long slot = static_cast<long long>(page) * page_size + pos % page_size;
+            const bool is_k = head < n_q + n_kv;
+            const int kvh = is_k ? head - n_q : head - n_q - n_kv;
+            __nv_bfloat16* dst = (is_k ? k_cache : v_cache) + (slot * n_kv + kvh) * 128;
+            dst[j] = __float2bfloat16(s0);
+            dst[j + 64] = __float2bfloat16(s1);
+        }
+    }
+    __device__ void finalize(int, FinishState&, float*) const {}
+};
+
+struct OProjOp {
+    const __nv_bfloat16* x;  // [B, K] attention output
+    const __nv_bfloat16* w;  // [N, K]
+    __nv_bfloat16* h;        // [B, N] residual stream, updated in place
+    int K, N;
+
+    __device__ int x_elems() const { return K; }
+    __device__ bool x_per_row() const { return false; }
+    __device__ long long num_items() const { return N / 2; }
+    __device__ const __nv_bfloat16* row_ptr(int, int item, int r) const {
+        return w + static_cast<long long>(item * 2 + r) * K;
+    }
+    __device__ void load_x(int b, __nv_bfloat16* xs, float*) const { load_x_copy(x + static_cast<long long>(b) * K, xs, K); }
+    __device__ void finish(int b, int item, float s0, float s1, FinishState&) const {
+        __nv_bfloat16* hr = h + static_cast<long long>(b) * N + item * 2;
+        hr[0] = __float2bfloat16(__bfloat162float(hr[0]) + s0);
+        hr[1] = __float2bfloat16(__bfloat162float(hr[1]) + s1);
+    }
+    __device__ void finalize(int, FinishState&, float*) const {}
+};
+
+struct GateUpOp {
+    const __nv_bfloat16* xn;     // [B, H] normed activations (written by the router kernel)
+    const __nv_bfloat16* w13;    // [E, 2I, H]
+    const int* topk_ids;         // [B, 2]
+    __nv_bfloat16* act;          // [B, 2, I]
+    int K, I;
+
+    __device__ int x_elems() const { return K; }
+    __device__ bool x_per_row() const { return false; }
+    __device__ long long num_items() const { return 2ll * I; }
+    __device__ const __nv_bfloat16* row_ptr(int b, int item, int r) const {
+        const int k = item / I, j = item % I;
+        const int e = topk_ids[b * 2 + k];
+        return w13 + (static_cast<long long>(e) * 2 * I + r * I + j) * K;
+    }
+    __device__ void load_x(int b, __nv_bfloat16* xs, float*) const { load_x_copy(xn + static_cast<long long>(b) * K, xs, K); }
+    __device__ void finish(int b, int item, float s0, float s1, FinishState&) const {
+        // gate and up are bf16 linear outputs in the reference; silu(gate) * up in fp32, one rounding
+        act[static_cast<long long>(b) * 2 * I + item] = __float2bfloat16(silu(s0) * s1);
+    }
+    __device__ void finalize(int, FinishState&, float*) const {}
+};
+
+struct DownOp {
+    const __nv_bfloat16* act;   // [B, 2, I]
+    const __nv_bfloat16* w2;    // [E, H, I]
+    const int* topk_ids;        // [B, 2]
+    const float* topk_w;        // [B, 2]
+    __nv_bfloat16* h;           // [B, H] residual stream, updated in place
+    int K, H;                   // K = I
+
+    __device__ int x_elems() const { return 2 * K; }
+    __device__ bool x_per_row() const { return true; }
+    __device__ long long num_items() const { return H; }
+    __device__ const __nv_bfloat16* row_ptr(int b, int item, int r) const {
+        const int e = topk_ids[b * 2 + r];
+        return w2 + (static_cast<long long>(e) * H + item) * K;
+    }
+    __device__ void load_x(int b, __nv_bfloat16* xs, float*) const {
+        load_x_copy(act + static_cast<long long>(b) * 2 * K, xs, 2 * K);
+    }
+    __device__ void finish(int b, int item, float s0, float s1, FinishState&) const {
+        __nv_bfloat16* hr = h + static_cast<long long>(b) * H + item;
+        const float y = topk_w[b * 2] * s0 + topk_w[b * 2 + 1] * s1;
+        hr[0] = __float2bfloat16(__bfloat162float(hr[0]) + y);
+    }
+    __device__ void finalize(int, FinishState&, float*) const {}
+};
+
+__device__ __forceinline__ unsigned long long pack_argmax(float v, int idx) {
+    uint32_t u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(idx));
+}
+
+struct LmHeadOp {
+    const __nv_bfloat16* h;        // rows of the residual stream, row b at h + b * h_stride
+    long long h_stride;
+    const __nv_bfloat16* norm_w;   // final RMSNorm
+    const __nv_bfloat16* w;        // [V, K]
+    __nv_bfloat16* logits;         // [B, V] or nullptr
+    unsigned long long* best;      // [B] packed (value, ~index), reset to 0 before the step
+    int K, V;
+    float eps;
+
+    __device__ int x_elems() const { return K; }
+    __device__ bool x_per_row() const { return false; }
+    __device__ long long num_items() const { return (V + 1) / 2; }
+    __device__ const __nv_bfloat16* row_ptr(int, int item, int r) const {
+        int row = item * 2 + r;
+        if (row >= V) row = V - 1;
+        return w + static_cast<long long>(row) * K;
+    }
+    __device__ void load_x(int b, __nv_bfloat16* xs, float* red8) const {
+        load_x_rmsnorm(h + static_cast<long long>(b) * h_stride, norm_w, xs, K, eps, red8);
+    }
+    __device__ void finish(int b, int item, float s0, float s1, FinishState& st) const {
+        const int r0 = item * 2, r1 = item * 2 + 1;
+        // logits stay in the activation dtype and arg-max runs on them (vita_mixtral.py:171-173)
+        const __nv_bfloat16 l0 = __float2bfloat16(s0), l1 = __float2bfloat16(s1);
+        if (logits) {
+            logits[static_cast<long long>(b) * V + r0] = l0;
+            if (r1 < V) logits[static_cast<long long>(b) * V + r1] = l1;
+        }
+        const float f0 = __bfloat162float(l0), f1 = __bfloat162float(l1);
+        if (f0 > st.best || (f0 == st.best && r0 < st.best_idx)) { st.best = f0; st.best_idx = r0; }
+        if (r1 < V && (f1 > st.best || (f1 == st.best && r1 < st.best_idx))) { st.best = f1; st.best_idx = r1; }
+    }
+    __device__ void finalize(int b, FinishState& st, float*) const {
+        if ((threadIdx.x & 31) == 0 && st.best_idx != 0x7fffffff) atomicMax(&best[b], pack_argmax(st.best, st.best_idx));
+    }
+};
+
+template <class Op>
+static int launch_stream_gemv(const Op& op, int x_elems, int B, cudaStream_t st, const char* name) {
+    const int smem_bytes = GV_STAGES * GV_STAGE_BYTES + ((x_elems * 2 + 127) / 128) * 128 + 2 * GV_STAGES * 8 +
+                           (32 + 8) * 4 + 256;
+    auto kern = stream_gemv_kernel<Op>;
+    static int configured_bytes = 0;
+    if (smem_bytes > configured_bytes) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), name);
+        if (rc) return rc;
+        configured_bytes = smem_bytes;
+    }
+    dim3 grid(num_sms(), B);
+    kern<<<grid, GV_THREADS, smem_bytes, st>>>(op);
+    return check_launch(name);
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// Start of a decode step: consume the previous arg-max, log it, advance the cache length, gather the embedding.
+__global__ void __launch_bounds__(256)
+decode_embed_kernel(unsigned long long* best, int* token_log, int* gen_count, int max_log, int* cache_len,
+                    int* cur_pos, const __nv_bfloat16* embed, __nv_bfloat16* h, int H, int vocab) {
+    const int b = blockIdx.x;
+    __shared__ int s_tok;
+    if (threadIdx.x == 0) {
+        const unsigned long long key = best[b];
+        int tok = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull));
+        if (tok < 0 || tok >= vocab) tok = 0;
+        s_tok = tok;
+        const int n = gen_count[b];
+        if (n < max_log) token_log[static_cast<long long>(b) * max_log + n] = tok;
+        gen_count[b] = n + 1;
+        cur_pos[b] = cache_len[b];
+        cache_len[b] = cache_len[b] + 1;
+        best[b] = 0ull;
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(embed + static_cast<long long>(s_tok) * H);
+    uint4* dst = reinterpret_cast<uint4*>(h + static_cast<long long>(b) * H);
+    for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) dst[i] = src[i];
+}
+
+// post_attention_layernorm + router for one token per block (E = 8 warps).
+__global__ void __launch_bounds__(256)
+decode_router_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ norm_w,
+                     const __nv_bfloat16* __restrict__ gate_w, __nv_bfloat16* __restrict__ xn,
+                     int* __restrict__ topk_ids, float* __restrict__ topk_w, int H, float eps) {
+    extern __shared__ __align__(16) uint8_t smem_r[];
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_r);
+    __shared__ float red[8];
+    __shared__ float logits[8];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const __nv_bfloat16* hr = h + static_cast<long long>(b) * H;
+    float ss = 0.0f;
+    for (int i = threadIdx.x; i < H; i += 256) { const float v = __bfloat162float(hr[i]); ss += v * v; }
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float tot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float inv = rsqrtf(tot / static_cast<float>(H) + eps);
+    for (int i = threadIdx.x; i < H; i += 256) {
+        const __nv_bfloat16 v = __float2bfloat16(__bfloat162float(hr[i]) * inv * __bfloat162float(norm_w[i]));
+        xs[i] = v;
+        xn[static_cast<long long>(b) * H + i] = v;
+    }
+    __syncthreads();
+    float acc = 0.0f;
+    const __nv_bfloat16* gw = gate_w + static_cast<long long>(warp) * H;
+    for (int i = lane * 8; i < H; i += 256) {
+        const uint4 w = *reinterpret_cast<const uint4*>(gw + i);
+        const uint4 x = *reinterpret_cast<const uint4*>(xs + i);
+        const uint32_t wa[4] = {w.x, w.y, w.z, w.w}, xa[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc += bf16_lo(wa[e]) * bf16_lo(xa[e]) + bf16_hi(wa[e]) * bf16_hi(xa[e]);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) logits[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = -INFINITY;
+        for (int e = 0; e < 8; ++e) m = fmaxf(m, logits[e]);
+        float p[8], sum = 0.0f;
+        for (int e = 0; e < 8; ++e) { p[e] = expf(logits[e] - m); sum += p[e]; }
+        int i0 = 0;
+        for (int e = 1; e < 8; ++e) if (p[e] > p[i0]) i0 = e;
+        int i1 = (i0 == 0) ? 1 : 0;
+        for (int e = 0; e < 8; ++e) if (e != i0 && p[e] > p[i1]) i1 = e;
+        const float p0 = p[i0] / sum, p1 = p[i1] / sum, den = p0 + p1;
+        topk_ids[b * 2] = i0;
+        topk_ids[b * 2 + 1] = i1;
+        topk_w[b * 2] = p0 / den;
+        topk_w[b * 2 + 1] = p1 / den;
+    }
+}
+
+}  // namespace vita
+
+using namespace vita;
+
+extern "C" int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* gen_count, int64_t max_log,
+                                 int32_t* cache_len, int32_t* cur_pos, const void* embed, void* h, int64_t B,
+                                 int64_t H, int64_t vocab, void* stream) {
+    VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    if (B == 0) return VITA_OK;
+    decode_embed_kernel<<<static_cast<unsigned>(B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<unsigned long long*>(best), token_log, gen_count, (int)max_log, cache_len, cur_pos,
+        BF16C(embed), static_cast<__nv_bfloat16*>(h), (int)H, (int)vocab);
+    return check_launch("decode_embed");
+}
+
+extern "C" int vita_decode_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, const float* cos_sin,
+                                    const int32_t* cur_pos, const int32_t* block_table, void* q_out, void* k_cache,
+                                    void* v_cache, int64_t B, int64_t H, int64_t n_q_heads, int64_t n_kv_heads,
+                                    int64_t head_dim, int64_t page_size, int64_t max_pages, float eps, void* stream) {
+    VITA_REQUIRE(head_dim == 128, "head_dim must be 128");
+    VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    if (B == 0) return VITA_OK;
+    QkvOp op{BF16C(h), BF16C(norm_w), BF16C(w_qkv), cos_sin, cur_pos, block_table, static_cast<__nv_bfloat16*>(q_out),
+             static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), (int)H, (int)n_q_heads,
+             (int)n_kv_heads, (int)page_size, (int)max_pages, eps};
+    return launch_stream_gemv(op, (int)H, (int)B, static_cast<cudaStream_t>(stream), "decode_qkv_rope");
+}
+
+extern "C" int vita_decode_oproj(const void* x, const void* w, void* h, int64_t B, int64_t N, int64_t K,
+                                 void* stream) {
+    VITA_REQUIRE(K % 8 == 0 && N % 2 == 0, "K must be a multiple of 8 and N even");
+    if (B == 0) return VITA_OK;
+    OProjOp op{BF16C(x), BF16C(w), static_cast<__nv_bfloat16*>(h), (int)K, (int)N};
+    return launch_stream_gemv(op, (int)K, (int)B, static_cast<cudaStream_t>(stream), "decode_oproj");
+}
+
+extern "C" int vita_decode_router(const void* h, const void* norm_w, const void* gate_w, void* xn, int32_t* topk_ids,
+                                  float* topk_w, int64_t B, int64_t H, int64_t E, float eps, void* stream) {
+    VITA_REQUIRE(E == 8, "router is specialised for 8 experts (Mixtral-8x7B)");
+    VITA_REQUIRE(H % 8 == 0 && H * 2 <= 48 * 1024, "H must be a multiple of 8 and fit 48 KB of shared memory");
+    if (B == 0) return VITA_OK;
+    decode_router_kernel<<<static_cast<unsigned>(B), 256, H * 2, static_cast<cudaStream_t>(stream)>>>(
+        BF16C(h), BF16C(norm_w), BF16C(gate_w), static_cast<__nv_bfloat16*>(xn), topk_ids, topk_w, (int)H, eps);
+    return check_launch("decode_router");
+}
+
+extern "C" int vita_decode_moe_gate_up(const void* xn, const void* w13, const int32_t* topk_ids, void* act, int64_t B,
+                                       int64_t H, int64_t I, void* stream) {
+    VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    if (B == 0) return VITA_OK;
+    GateUpOp op{BF16C(xn), BF16C(w13), topk_ids, static_cast<__nv_bfloat16*>(act), (int)H, (int)I};
+    return launch_stream_gemv(op, (int)H, (int)B, static_cast<cudaStream_t>(stream), "decode_moe_gate_up");
+}
+
+extern "C" int vita_decode_moe_down(const void* act, const void* w2, const int32_t* topk_ids, const float* topk_w,
+                                    void* h, int64_t B, int64_t H, int64_t I, void* stream) {
+    VITA_REQUIRE(I % 8 == 0, "I must be a multiple of 8");
+    if (B == 0) return VITA_OK;
+    DownOp op{BF16C(act), BF16C(w2), topk_ids, topk_w, static_cast<__nv_bfloat16*>(h), (int)I, (int)H};
+    return launch_stream_gemv(op, (int)(2 * I), (int)B, static_cast<cudaStream_t>(stream), "decode_moe_down");
+}
+
+extern "C" int vita_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
+                                   uint64_t* best, int64_t B, int64_t H, int64_t V, float eps, void* stream) {
+    VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    if (B == 0) return VITA_OK;
+    LmHeadOp op{BF16C(h), h_stride, BF16C(norm_w), BF16C(w), static_cast<__nv_bfloat16*>(logits),
+                reinterpret_cast<unsigned long long*>(best), (int)H, (int)V, eps};
+    return launch_stream_gemv(op, (int)H, (int)B, static_cast<cudaStream_t>(stream), "lm_head_argmax");
+}

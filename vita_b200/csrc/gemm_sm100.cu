@@ -1,0 +1,425 @@
+// bf16 "TN" GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . B[N,K]^T), fp32 accumulation in TMEM.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1   : MMA issuer    (one thread, tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16 per instruction)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> 64 B vector stores)
+// The accumulator is double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  The same kernel serves the plain linears (ViT / Whale / projector / Mixtral qkv,o) and the
+// grouped expert GEMMs of the MoE (ragged row groups given by a device-side offsets array, no host sync).
+//
+// Reference call sites this replaces (all nn.Linear / F.linear -> cuBLAS in the reference):
+//   vita/model/multimodal_encoder/internvit/modeling_intern_vit.py:180,192,214,216
+//   vita/model/multimodal_encoder/whale/module/layer/attention.py:371-373,381,419 ; :145-147
+//   vita/model/multimodal_projector/builder.py:164-168
+//   transformers MixtralAttention q/k/v/o_proj, MixtralExperts.forward (gate_up_proj / down_proj)
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vita {
+
+struct GemmArgs {
+    int M;                      // rows of A / C (total over groups)
+    int N;                      // output columns (per group)
+    int K;
+    int num_groups;             // >= 1
+    const int* group_offsets;   // device [num_groups + 1] row offsets, or nullptr (single group = all rows)
+    __nv_bfloat16* C;
+    long long ldc;
+    const __nv_bfloat16* bias;  // [num_groups, N] or nullptr
+    const __nv_bfloat16* colscale;  // [N] or nullptr   (InternViT layer-scale ls1/ls2)
+    const float* rowscale;          // [M] or nullptr   (MoE routing weight)
+    const __nv_bfloat16* residual;  // [M, ldr] or nullptr
+    long long ldr;
+    int act;                    // VITA_ACT_*
+};
+
+struct Tile {
+    int group, m0, m_end, n0;
+};
+
+// Tile order inside a group: n-block major, m-block minor, so CTAs that run together share the weight tile in L2.
+template <int BN_OUT>
+__device__ __forceinline__ bool tile_at(const GemmArgs& a, int tile_idx, Tile& t) {
+    const int num_n = (a.N + BN_OUT - 1) / BN_OUT;
+    int base = 0;
+    for (int g = 0; g < a.num_groups; ++g) {
+        const int r0 = a.group_offsets ? a.group_offsets[g] : 0;
+        const int r1 = a.group_offsets ? a.group_offsets[g + 1] : a.M;
+        const int mt = (r1 - r0 + 127) >> 7;
+        const int nt = mt * num_n;
+        if (tile_idx < base + nt) {
+            const int local = tile_idx - base;
+            t.group = g;
+            t.n0 = (local / mt) * BN_OUT;
+            t.m0 = r0 + (local % mt) * 128;
+            t.m_end = r1;
+            return true;
+        }
+        base += nt;
+    }
+    return false;
+}
+
+template <int BLOCK_N, bool SILU, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs args) {
+    constexpr int BLOCK_M = 128, BLOCK_K = 64;
+    constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int BN_OUT = SILU ? BLOCK_N / 2 : BLOCK_N;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = (args.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            Tile t;
+            for (int tile = blockIdx.x; tile_at<BN_OUT>(args, tile, t); tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+                    tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, t.m0);
+                    if constexpr (SILU) {
+                        // gate rows [n0, n0+128) and up rows [N + n0, N + n0 + 128) of the fused [2N, K] weight
+                        tma_load_3d(sB + stage * B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, t.n0, t.group);
+                        tma_load_3d(sB + stage * B_BYTES + B_BYTES / 2, &tmB, &full_bar[stage], kb * BLOCK_K,
+                                    args.N + t.n0, t.group);
+                    } else {
+                        tma_load_3d(sB + stage * B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, t.n0, t.group);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+            Tile t;
+            for (int tile = blockIdx.x; tile_at<BN_OUT>(args, tile, t); tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k_sw128(sA_addr + stage * A_BYTES);
+                    const uint64_t db = umma_desc_k_sw128(sB_addr + stage * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16 B units
+                        tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);
+                    if (kb == num_kb - 1) tc_commit(&tmem_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue
+        const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        Tile t;
+        for (int tile = blockIdx.x; tile_at<BN_OUT>(args, tile, t); tile += gridDim.x) {
+            mbar_wait(&tmem_full[acc], acc_phase, 4);
+            tc_fence_after();
+            const int grow = t.m0 + quad * 32 + lane;
+            const bool valid = grow < t.m_end;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+            const float rs = (args.rowscale && valid) ? args.rowscale[grow] : 1.0f;
+            const __nv_bfloat16* bias = args.bias ? args.bias + static_cast<long long>(t.group) * args.N : nullptr;
+            __nv_bfloat16* crow = args.C + static_cast<long long>(grow) * args.ldc;
+            const __nv_bfloat16* rrow = args.residual ? args.residual + static_cast<long long>(grow) * args.ldr : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BN_OUT / 32; ++c) {
+                const int col0 = t.n0 + c * 32;
+                if (col0 >= args.N) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c * 32, v);
+                if constexpr (SILU) {
+                    uint32_t u[32];
+                    tmem_ld_32x32(taddr + BN_OUT + c * 32, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        v[j] = __float_as_uint(silu(__uint_as_float(v[j])) * __uint_as_float(u[j]));
+                } else {
+                    tmem_ld_wait();
+                }
+                const bool full_chunk = (col0 + 32 <= args.N);
+                if (full_chunk) {
+                    // column-wise terms are identical for all lanes: broadcast loads
+                    if (bias) {
+                        const uint4* bp = reinterpret_cast<const uint4*>(bias + col0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 b = __ldg(bp + q);
+                            const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[q * 8 + e * 2] = __float_as_uint(__uint_as_float(v[q * 8 + e * 2]) + bf16_lo(w[e]));
+                                v[q * 8 + e * 2 + 1] =
+                                    __float_as_uint(__uint_as_float(v[q * 8 + e * 2 + 1]) + bf16_hi(w[e]));
+                            }
+                        }
+                    }
+                    if (args.act == VITA_ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
+                    } else if (args.act == VITA_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.0f));
+                    }
+                    if (args.colscale) {
+                        const uint4* sp = reinterpret_cast<const uint4*>(args.colscale + col0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 b = __ldg(sp + q);
+                            const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[q * 8 + e * 2] = __float_as_uint(__uint_as_float(v[q * 8 + e * 2]) * bf16_lo(w[e]));
+                                v[q * 8 + e * 2 + 1] =
+                                    __float_as_uint(__uint_as_float(v[q * 8 + e * 2 + 1]) * bf16_hi(w[e]));
+                            }
+                        }
+                    }
+                    if (valid) {
+                        if (args.rowscale) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
+                        }
+                        if (rrow) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(rrow + col0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 b = rp[q];
+                                const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    v[q * 8 + e * 2] =
+                                        __float_as_uint(__uint_as_float(v[q * 8 + e * 2]) + bf16_lo(w[e]));
+                                    v[q * 8 + e * 2 + 1] =
+                                        __float_as_uint(__uint_as_float(v[q * 8 + e * 2 + 1]) + bf16_hi(w[e]));
+                                }
+                            }
+                        }
+                        uint4* cp = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 o;
+                            o.x = pack_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                            o.y = pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                            o.z = pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                            o.w = pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                            cp[q] = o;
+                        }
+                    }
+                } else if (valid) {
+                    // ragged N tail: scalar path
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + j;
+                        if (col >= args.N) break;
+                        float x = __uint_as_float(v[j]);
+                        if (bias) x += __bfloat162float(bias[col]);
+                        if (args.act == VITA_ACT_GELU) x = gelu_erf(x);
+                        else if (args.act == VITA_ACT_RELU) x = fmaxf(x, 0.0f);
+                        if (args.colscale) x *= __bfloat162float(args.colscale[col]);
+                        x *= rs;
+                        if (rrow) x += __bfloat162float(rrow[col]);
+                        crow[col] = __float2bfloat16(x);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BLOCK_N, bool SILU, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int max_tiles,
+                       cudaStream_t stream) {
+    constexpr int smem_bytes = STAGES * (128 * 64 * 2 + BLOCK_N * 64 * 2) + 1024 + 256;
+    static bool configured = false;
+    auto kern = gemm_bf16_tn_kernel<BLOCK_N, SILU, STAGES>;
+    if (!configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
+                            "cudaFuncSetAttribute(gemm smem)");
+        if (rc) return rc;
+        configured = true;
+    }
+    int grid = num_sms();
+    if (max_tiles < grid) grid = max_tiles;
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, args);
+    return check_launch("gemm_bf16_tn_kernel");
+}
+
+// a_rows: number of valid rows in A (TMA zero-fills beyond); b: [num_groups, b_rows, K] contiguous.
+static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B, int b_rows, const GemmArgs& args,
+                         bool silu, cudaStream_t stream) {
+    VITA_REQUIRE(args.K > 0 && args.N > 0 && args.M >= 0, "bad shape");
+    VITA_REQUIRE(args.K % 8 == 0 && lda % 8 == 0, "K and lda must be multiples of 8 (16-byte TMA strides)");
+    VITA_REQUIRE(aligned16(A) && aligned16(B) && aligned16(args.C), "A, B, C must be 16-byte aligned");
+    VITA_REQUIRE(args.ldc % 8 == 0, "ldc must be a multiple of 8");
+    VITA_REQUIRE(!args.residual || (args.ldr % 8 == 0 && aligned16(args.residual)), "residual alignment");
+    VITA_REQUIRE(!args.bias || aligned16(args.bias), "bias alignment");
+    VITA_REQUIRE(!args.bias || args.num_groups == 1 || args.N % 8 == 0, "grouped bias needs N % 8 == 0");
+    VITA_REQUIRE(!args.colscale || aligned16(args.colscale), "colscale alignment");
+    if (args.M == 0) return VITA_OK;
+
+    const int n_sms = num_sms();
+    const long long m_tiles_ub = (args.M / 128) + args.num_groups;  // valid for any ragged split of M rows
+    int block_n;
+    if (silu) {
+        block_n = 256;
+    } else {
+        const long long tiles256 = m_tiles_ub * ((args.N + 255) / 256);
+        block_n = (tiles256 >= n_sms && args.N >= 256) ? 256 : 128;
+    }
+    const int bn_out = silu ? block_n / 2 : block_n;
+    const long long max_tiles_ll = m_tiles_ub * ((args.N + bn_out - 1) / bn_out);
+    const int max_tiles = max_tiles_ll > (1 << 30) ? (1 << 30) : static_cast<int>(max_tiles_ll);
+
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(args.K), static_cast<uint64_t>(a_rows)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+        const uint32_t box[2] = {64, 128};
+        int rc = make_tensor_map_bf16(&tmA, A, 2, dims, strides, box, true);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[3] = {static_cast<uint64_t>(args.K), static_cast<uint64_t>(b_rows),
+                                  static_cast<uint64_t>(args.num_groups)};
+        const uint64_t strides[2] = {static_cast<uint64_t>(args.K) * 2,
+                                     static_cast<uint64_t>(args.K) * 2 * static_cast<uint64_t>(b_rows)};
+        const uint32_t box[3] = {64, static_cast<uint32_t>(silu ? block_n / 2 : block_n), 1};
+        int rc = make_tensor_map_bf16(&tmB, B, 3, dims, strides, box, true);
+        if (rc) return rc;
+    }
+    if (silu) return launch_gemm<256, true, 4>(tmA, tmB, args, max_tiles, stream);
+    if (block_n == 256) return launch_gemm<256, false, 4>(tmA, tmB, args, max_tiles, stream);
+    return launch_gemm<128, false, 6>(tmA, tmB, args, max_tiles, stream);
+}
+
+}  // namespace vita
+
+using namespace vita;
+
+extern "C" int vita_gemm_bf16(const void* A, int64_t lda, const void* B, void* C, int64_t ldc, int64_t M, int64_t N,
+                              int64_t K, const void* bias, int act, const void* colscale, const void* residual,
+                              int64_t ldr, void* stream) {
+    GemmArgs a{};
+    a.M = static_cast<int>(M);
+    a.N = static_cast<int>(N);
+    a.K = static_cast<int>(K);
+    a.num_groups = 1;
+    a.group_offsets = nullptr;
+    a.C = static_cast<__nv_bfloat16*>(C);
+    a.ldc = ldc;
+    a.bias = static_cast<const __nv_bfloat16*>(bias);
+    a.colscale = static_cast<const __nv_bfloat16*>(colscale);
+    a.rowscale = nullptr;
+    a.residual = static_cast<const __nv_bfloat16*>(residual);
+    a.ldr = ldr;
+    a.act = act;
+    VITA_REQUIRE(act == VITA_ACT_NONE || act == VITA_ACT_GELU || act == VITA_ACT_RELU, "unknown activation");
+    return gemm_dispatch(A, lda, a.M, B, a.N, a, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vita_moe_gemm_gate_up_silu(const void* X_perm, const void* W_gate_up, void* Act,
+                                          const int32_t* expert_offsets, int64_t rows, int64_t num_experts,
+                                          int64_t H, int64_t I, void* stream) {
+    GemmArgs a{};
+    a.M = static_cast<int>(rows);
+    a.N = static_cast<int>(I);
+    a.K = static_cast<int>(H);
+    a.num_groups = static_cast<int>(num_experts);
+    a.group_offsets = expert_offsets;
+    a.C = static_cast<__nv_bfloat16*>(Act);
+    a.ldc = I;
+    a.act = VITA_ACT_NONE;
+    VITA_REQUIRE(expert_offsets != nullptr, "expert_offsets required");
+    VITA_REQUIRE(I % 8 == 0, "I must be a multiple of 8");
+    return gemm_dispatch(X_perm, H, a.M, W_gate_up, static_cast<int>(2 * I), a, true,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vita_moe_gemm_down(const void* Act, const void* W_down, void* Y_perm, const int32_t* expert_offsets,
+                                  const float* row_weight, int64_t rows, int64_t num_experts, int64_t H, int64_t I,
+                                  void* stream) {
+    GemmArgs a{};
+    a.M = static_cast<int>(rows);
+    a.N = static_cast<int>(H);
+    a.K = static_cast<int>(I);
+    a.num_groups = static_cast<int>(num_experts);
+    a.group_offsets = expert_offsets;
+    a.C = static_cast<__nv_bfloat16*>(Y_perm);
+    a.ldc = H;
+    a.rowscale = row_weight;
+    a.act = VITA_ACT_NONE;
+    VITA_REQUIRE(expert_offsets != nullptr, "expert_offsets required");
+    return gemm_dispatch(Act, I, a.M, W_down, static_cast<int>(H), a, false, static_cast<cudaStream_t>(stream));
+}
