@@ -1,0 +1,221 @@
+"""Mixtral-8x7B sparse-MoE decoder on the B200 kernels: paged KV cache, prefill, CUDA-graphed greedy decode.
+
+Replaces the third-party arithmetic the reference reaches through `self.model(...)` / `lm_head`
+(vita/model/language_model/vita_mixtral.py:158-173 -> transformers MixtralModel; vLLM twin
+web_demo/vllm_tools/vllm_file/mixtral.py:375-628).  Host code only sequences kernels; no arithmetic in torch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from .. import ops
+from ..config import LLMConfig
+
+BF16 = torch.bfloat16
+
+
+class PagedKVCache:
+    """k/v per layer: [num_pages * page_size, n_kv_heads, head_dim] bf16; block_table [max_batch, pages_per_seq]."""
+
+    def __init__(self, cfg: LLMConfig, max_batch: int, max_seq_len: int, device, page_size: int = 16,
+                 shuffle_pages: bool = False):
+        self.page_size = page_size
+        self.pages_per_seq = (max_seq_len + page_size - 1) // page_size
+        self.max_seq_len = self.pages_per_seq * page_size
+        self.max_batch = max_batch
+        n_pages = max_batch * self.pages_per_seq
+        slots = n_pages * page_size
+        shape = (slots, cfg.num_key_value_heads, cfg.head_dim)
+        self.k = [torch.zeros(shape, dtype=BF16, device=device) for _ in range(cfg.num_hidden_layers)]
+        self.v = [torch.zeros(shape, dtype=BF16, device=device) for _ in range(cfg.num_hidden_layers)]
+        order = torch.randperm(n_pages, generator=torch.Generator().manual_seed(0)) if shuffle_pages \
+            else torch.arange(n_pages)
+        table = order.view(max_batch, self.pages_per_seq).to(torch.int32)
+        self.block_table = table.to(device)
+        pos = torch.arange(self.max_seq_len)
+        self.slot_map = (table[:, pos // page_size].to(torch.int64) * page_size + (pos % page_size)[None, :]) \
+            .to(torch.int32).to(device)                                      # [max_batch, max_seq_len]
+        self.cache_len = torch.zeros(max_batch, dtype=torch.int32, device=device)
+        self.cur_pos = torch.zeros(max_batch, dtype=torch.int32, device=device)
+
+    def reset(self):
+        self.cache_len.zero_()
+        self.cur_pos.zero_()
+
+
+class MixtralDecoder:
+    def __init__(self, cfg: LLMConfig, weights: dict, device, max_batch: int = 1, max_seq_len: Optional[int] = None,
+                 max_new_tokens: int = 1024, page_size: int = 16, decode_splits: int = 16, shuffle_pages: bool = False):
+        self.cfg = cfg
+        self.w = weights
+        self.device = torch.device(device)
+        self.max_batch = max_batch
+        max_seq_len = max_seq_len or (cfg.tokenizer_model_max_length + max_new_tokens)
+        assert max_seq_len <= weights["rope"].shape[0], "rope table too short for max_seq_len"
+        self.cache = PagedKVCache(cfg, max_batch, max_seq_len, device, page_size, shuffle_pages)
+        self.max_new_tokens = max_new_tokens
+        self.decode_splits = decode_splits
+        H, I = cfg.hidden_size, cfg.intermediate_size
+        B = max_batch
+        dev = self.device
+        # decode-step state (all device resident: a step needs no host input, so it can be replayed as a CUDA graph)
+        self.best = torch.zeros(B, dtype=torch.int64, device=dev)         # packed (logit, ~index) arg-max
+        self.token_log = torch.zeros(B, max_new_tokens + 8, dtype=torch.int32, device=dev)
+        self.gen_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.d_h = torch.zeros(B, H, dtype=BF16, device=dev)
+        self.d_q = torch.zeros(B, cfg.num_attention_heads * cfg.head_dim, dtype=BF16, device=dev)
+        self.d_attn = torch.zeros_like(self.d_q)
+        self.d_xn = torch.zeros(B, H, dtype=BF16, device=dev)
+        self.d_ids = torch.zeros(B, 2, dtype=torch.int32, device=dev)
+        self.d_w = torch.zeros(B, 2, dtype=torch.float32, device=dev)
+        self.d_act = torch.zeros(B, 2, I, dtype=BF16, device=dev)
+        self.d_logits = torch.zeros(B, cfg.vocab_size, dtype=BF16, device=dev)
+        self.attn_ws = ops.decode_attention_workspace(B, cfg.num_key_value_heads, decode_splits, dev)
+        self._graph = None
+        self._graph_batch = None
+        self._prefill_ws = {}
+
+    # ------------------------------------------------------------------------------------------ prefill
+    def _ws(self, S: int):
+        """Prefill workspaces, grown geometrically and reused."""
+        cap = self._prefill_ws.get("cap", 0)
+        if S > cap:
+            c = self.cfg
+            cap = max(S, 2 * cap, 128)
+            H, I, E, dev = c.hidden_size, c.intermediate_size, c.num_local_experts, self.device
+            self._prefill_ws = dict(
+                cap=cap,
+                xn=torch.empty(cap, H, dtype=BF16, device=dev),
+                qkv=torch.empty(cap, c.qkv_rows, dtype=BF16, device=dev),
+                attn=torch.empty(cap, c.num_attention_heads * c.head_dim, dtype=BF16, device=dev),
+                xn2=torch.empty(cap, H, dtype=BF16, device=dev),
+                ids=torch.empty(cap, 2, dtype=torch.int32, device=dev),
+                tw=torch.empty(cap, 2, dtype=torch.float32, device=dev),
+                offs=torch.empty(E + 1, dtype=torch.int32, device=dev),
+                perm=torch.empty(cap * 2, dtype=torch.int32, device=dev),
+                rtok=torch.empty(cap * 2, dtype=torch.int32, device=dev),
+                rw=torch.empty(cap * 2, dtype=torch.float32, device=dev),
+                xp=torch.empty(cap * 2, H, dtype=BF16, device=dev),
+                act=torch.empty(cap * 2, I, dtype=BF16, device=dev),
+                yp=torch.empty(cap * 2, H, dtype=BF16, device=dev),
+                pos=torch.arange(cap, dtype=torch.int32, device=dev))
+        return self._prefill_ws
+
+    @torch.no_grad()
+    def prefill(self, inputs_embeds: torch.Tensor, slot: int = 0, all_logits: bool = False,
+                want_last_logits: bool = False):
+        """One sequence: inputs_embeds [S, H] bf16 (consumed as the residual stream, modified in place).
+
+        Appends S tokens to the KV cache of batch slot `slot` (which must be empty), leaves the arg-max of the last
+        position in self.best[slot] (the first generated token) and returns logits [S, V] if `all_logits`."""
+        c, w = self.cfg, self.w
+        S, H = inputs_embeds.shape
+        assert inputs_embeds.dtype == BF16 and inputs_embeds.is_cuda and inputs_embeds.is_contiguous()
+        assert S <= self.cache.max_seq_len
+        ws = self._ws(S)
+        h = inputs_embeds
+        nq, nkv, D, E = c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.num_local_experts
+        xn, qkv, attn, xn2 = ws["xn"][:S], ws["qkv"][:S], ws["attn"][:S], ws["xn2"][:S]
+        ids, tw = ws["ids"][:S], ws["tw"][:S]
+        perm, rtok, rw = ws["perm"][:2 * S], ws["rtok"][:2 * S], ws["rw"][:2 * S]
+        xp, act, yp = ws["xp"][:2 * S], ws["act"][:2 * S], ws["yp"][:2 * S]
+        pos = ws["pos"][:S]
+        slots = self.cache.slot_map[slot, :S]
+        W = c.qkv_rows
+        layers = w["layers"]
+        ops.rmsnorm(h, layers[0]["ln1"], c.rms_norm_eps, out=xn)
+        for li, lw in enumerate(layers):
+            ops.linear(xn, lw["wqkv"], out=qkv)
+            ops.rope_kv_write(qkv, pos, slots, w["rope"], self.cache.k[li], self.cache.v[li], nq, nkv, D)
+            ops.attention(qkv, qkv[:, nq * D:], qkv[:, (nq + nkv) * D:], attn, (0, W, D), (0, W, D), (0, W, D),
+                          (0, nq * D, D), 1, nq, nkv, S, S, D, D, None, True, D ** -0.5)
+            ops.linear(attn, lw["wo"], residual=h, out=h)
+            ops.moe_router(h, lw["ln2"], lw["gate"], xn2, ids, tw, c.rms_norm_eps)
+            ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, S, E)
+            ops.row_copy(xn2, rtok, None, xp, 2 * S)
+            ops.moe_gate_up(xp, lw["w13"], act, ws["offs"], 2 * S)
+            ops.moe_down(act, lw["w2"], yp, ws["offs"], rw, 2 * S)
+            nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else (w["norm"] if all_logits else None)
+            ops.moe_combine(h, yp, perm, nxt, xn if nxt is not None else None, c.rms_norm_eps)
+        self.cache.cache_len[slot:slot + 1] += S
+        # first generated token: final norm + lm_head + arg-max on the last row only
+        self.best[slot:slot + 1].zero_()
+        last_logits = self.d_logits[slot:slot + 1] if (want_last_logits or all_logits) else None
+        ops.lm_head_argmax(h[S - 1:], H, w["norm"], w["lm_head"], last_logits, self.best[slot:slot + 1], 1,
+                           c.rms_norm_eps)
+        if all_logits:
+            return ops.linear(xn, w["lm_head"])      # [S, V]; xn = final RMSNorm(h) written by the last combine
+        return last_logits
+
+    # ------------------------------------------------------------------------------------------ decode
+    def _decode_step_kernels(self, B: int, want_logits: bool):
+        c, w, cache = self.cfg, self.w, self.cache
+        nq, nkv, D = c.num_attention_heads, c.num_key_value_heads, c.head_dim
+        h = self.d_h[:B]
+        ops.decode_embed(self.best[:B], self.token_log[:B], self.gen_count[:B], cache.cache_len[:B], cache.cur_pos[:B],
+                         w["embed"], h)
+        for li, lw in enumerate(w["layers"]):
+            ops.decode_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
+                                self.d_q[:B], cache.k[li], cache.v[li], nq, nkv, D, cache.page_size, c.rms_norm_eps)
+            ops.decode_attention(self.d_q[:B], cache.k[li], cache.v[li], cache.block_table[:B], cache.cur_pos[:B],
+                                 self.d_attn[:B], self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits,
+                                 D ** -0.5)
+            ops.decode_oproj(self.d_attn[:B], lw["wo"], h)
+            ops.decode_router(h, lw["ln2"], lw["gate"], self.d_xn[:B], self.d_ids[:B], self.d_w[:B], c.rms_norm_eps)
+            ops.decode_moe_gate_up(self.d_xn[:B], lw["w13"], self.d_ids[:B], self.d_act[:B])
+            ops.decode_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h)
+        ops.lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], self.d_logits[:B] if want_logits else None,
+                           self.best[:B], B, c.rms_norm_eps)
+
+    @property
+    def launches_per_decode_step(self) -> int:
+        return 2 + 6 * self.cfg.num_hidden_layers
+
+    @torch.no_grad()
+    def decode_step(self, B: int = 1, use_graph: bool = True, want_logits: bool = False):
+        """Generate one token for batch slots [0, B): consumes self.best, appends to token_log, leaves the next
+        arg-max in self.best.  With use_graph the whole step (2 + 6 * layers kernels) replays as one CUDA graph."""
+        if not use_graph:
+            self._decode_step_kernels(B, want_logits)
+            return
+        key = (B, want_logits)
+        if self._graph is None or self._graph_batch != key:
+            # capture (the kernels were warmed up by an eager step so every cudaFuncSetAttribute already ran)
+            self._snapshot = self._save_state()
+            self._decode_step_kernels(B, want_logits)
+            torch.cuda.synchronize()
+            self._restore_state(self._snapshot)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    self._decode_step_kernels(B, want_logits)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._restore_state(self._snapshot)   # capture does not execute, but keep the invariant explicit
+            self._graph, self._graph_batch = g, key
+        self._graph.replay()
+
+    def _save_state(self):
+        c = self.cache
+        return (self.best.clone(), self.gen_count.clone(), c.cache_len.clone(), c.cur_pos.clone(), self.d_h.clone(),
+                self.token_log.clone())
+
+    def _restore_state(self, s):
+        c = self.cache
+        self.best.copy_(s[0]); self.gen_count.copy_(s[1]); c.cache_len.copy_(s[2]); c.cur_pos.copy_(s[3])
+        self.d_h.copy_(s[4]); self.token_log.copy_(s[5])
+        # the KV slot written by the warm-up step is rewritten by the real step (same position): nothing to undo
+
+    def reset(self):
+        self.cache.reset()
+        self.best.zero_()
+        self.gen_count.zero_()
+        self.token_log.zero_()
+
+    def generated_tokens(self, slot: int = 0) -> List[int]:
+        n = int(self.gen_count[slot])
+        return self.token_log[slot, :n].tolist()

@@ -1,0 +1,284 @@
+"""`VITAMixtralForCausalLM` on the B200 kernels -- the reference's Python surface for the omni forward path.
+
+Mirrors vita/model/language_model/vita_mixtral.py:232-415 + vita/model/vita_arch.py:111-407:
+`forward`, `generate`, `encode_images`, `encode_audios`, `prepare_inputs_labels_for_multimodal`, `get_vision_tower`,
+`get_audio_encoder`, `process_images`.  The Python per-sample splice loop of the reference becomes host-side index
+arithmetic (`plan_splice`, pure Python, unit-tested on CPU) + three device row-copies.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from .. import ops
+from ..config import VitaConfig, IMAGE_TOKEN_INDEX, AUDIO_TOKEN_INDEX
+from .internvit import InternViTVisionTower, VisionProjector
+from .mixtral import MixtralDecoder
+from .whale import AudioEncoder
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ splice planning
+@dataclass
+class SplicePlan:
+    lengths: List[int]            # spliced length per sample (after truncation)
+    text_src: List[int]           # token ids to gather from embed_tokens
+    text_dst: List[int]           # flat destination row (sample * max_len + position)
+    img_src: List[int]            # flat row in image_features.view(-1, H)
+    img_dst: List[int]
+    aud_src: List[int]            # flat row in audio_features.view(-1, H)
+    aud_dst: List[int]
+    max_len: int
+
+
+def plan_splice(input_ids: Sequence[Sequence[int]], n_image_features: int, image_tokens: int, n_audio_features: int,
+                audio_tokens: int, max_model_len: Optional[int]) -> SplicePlan:
+    """Index arithmetic of prepare_inputs_labels_for_multimodal (vita/model/vita_arch.py:227-392), inference subset.
+
+    Every IMAGE (-200) / AUDIO (-500) placeholder is replaced by the next unused feature block
+    (`image_tokens` / `audio_tokens` rows each); samples lacking a modality still consume one (dummy) feature block
+    of it (:240-251, :309-316); the result is truncated to `max_model_len` (:326-329) and right-padded (:372-392).
+    Raises AssertionError on the same count mismatches the reference asserts (:227-236, :323-324)."""
+    n_img_ph = sum(sum(1 for t in row if t == IMAGE_TOKEN_INDEX) for row in input_ids)
+    n_aud_ph = sum(sum(1 for t in row if t == AUDIO_TOKEN_INDEX) for row in input_ids)
+    no_img = sum(1 for row in input_ids if IMAGE_TOKEN_INDEX not in row)
+    no_aud = sum(1 for row in input_ids if AUDIO_TOKEN_INDEX not in row)
+    assert n_img_ph + no_img == n_image_features, "image placeholder / feature count mismatch (vita_arch.py:227-231)"
+    assert n_aud_ph + no_aud == n_audio_features, "audio placeholder / feature count mismatch (vita_arch.py:232-236)"
+    per_sample = []
+    ii = ai = 0
+    for row in input_ids:
+        items = []   # (kind, value): ("t", token) | ("i", feature idx) | ("a", feature idx)
+        has_i = has_a = False
+        for t in row:
+            if t == IMAGE_TOKEN_INDEX:
+                items.append(("i", ii)); ii += 1; has_i = True
+            elif t == AUDIO_TOKEN_INDEX:
+                items.append(("a", ai)); ai += 1; has_a = True
+            else:
+                items.append(("t", int(t)))
+        if not has_i:
+            ii += 1      # a dummy image feature is consumed as a zero-length slice
+        if not has_a:
+            ai += 1
+        per_sample.append(items)
+    assert ii == n_image_features and ai == n_audio_features
+    plan = SplicePlan([], [], [], [], [], [], [], 0)
+    rows_per_sample = []
+    for items in per_sample:
+        rows = []
+        for kind, v in items:
+            if kind == "t":
+                rows.append(("t", v))
+            elif kind == "i":
+                rows.extend(("i", v * image_tokens + j) for j in range(image_tokens))
+            else:
+                rows.extend(("a", v * audio_tokens + j) for j in range(audio_tokens))
+        if max_model_len is not None:
+            rows = rows[:max_model_len]
+        rows_per_sample.append(rows)
+        plan.lengths.append(len(rows))
+    plan.max_len = max(plan.lengths) if plan.lengths else 0
+    for s, rows in enumerate(rows_per_sample):
+        for p, (kind, v) in enumerate(rows):
+            dst = s * plan.max_len + p
+            if kind == "t":
+                plan.text_src.append(v); plan.text_dst.append(dst)
+            elif kind == "i":
+                plan.img_src.append(v); plan.img_dst.append(dst)
+            else:
+                plan.aud_src.append(v); plan.aud_dst.append(dst)
+    return plan
+
+
+@dataclass
+class CausalLMOutput:
+    logits: Optional[torch.Tensor]
+    past_key_values: object = None
+
+
+@dataclass
+class GenerateOutput:
+    sequences: torch.Tensor
+    scores: Optional[tuple] = None
+
+
+class VITAMixtralForCausalLM:
+    """Inference-only drop-in for the reference class of the same name (no nn.Module: weights live in the packed
+    kernel-native layout)."""
+
+    def __init__(self, cfg: VitaConfig, packed: dict, device="cuda", max_batch: int = 1,
+                 max_seq_len: Optional[int] = None, max_new_tokens: int = 1024, shuffle_pages: bool = False):
+        self.config = cfg
+        self.device = torch.device(device)
+        self.dtype = BF16
+        self.packed = packed
+        self.llm = MixtralDecoder(cfg.llm, packed["llm"], device, max_batch, max_seq_len, max_new_tokens,
+                                  shuffle_pages=shuffle_pages)
+        self.vision_tower = InternViTVisionTower(cfg.vision, packed["vision"], device) if "vision" in packed else None
+        self.mm_projector = VisionProjector(packed["projector"]) if "projector" in packed else None
+        self.audio_encoder = AudioEncoder(cfg.audio, cfg.llm.hidden_size, packed["audio"], device) \
+            if "audio" in packed else None
+
+    # -- surface helpers ------------------------------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def get_model(self):
+        return self
+
+    def get_vision_tower(self):
+        return self.vision_tower
+
+    def get_audio_encoder(self):
+        return self.audio_encoder
+
+    def resize_token_embeddings(self, n: int):
+        assert n == self.config.llm.vocab_size, "vita_b200 does not resize packed embeddings"
+
+    def process_images(self, images, model_cfg=None):
+        """CPU preprocessing (vita_mixtral.py:397-415) is left to the caller's CLIPImageProcessor; tensors pass through."""
+        if isinstance(images, (list, tuple)):
+            return torch.stack([torch.as_tensor(im) for im in images])
+        return images
+
+    # -- encoders --------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_images(self, images: torch.Tensor) -> torch.Tensor:
+        """vita_arch.py:131-134: vision tower + mm_projector -> [N, 256, H]."""
+        return self.mm_projector(self.vision_tower(images))
+
+    @torch.no_grad()
+    def encode_audios(self, audios: torch.Tensor, lengths: torch.Tensor) -> dict:
+        """The call north_star names `encode_audios` (reference call site vita_arch.py:186-191)."""
+        return self.audio_encoder(audios, lengths)
+
+    # -- splice ----------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
+                                             images, audios):
+        """vita_arch.py:151-407.  Returns (None, position_ids, attention_mask, past_key_values, inputs_embeds, labels)."""
+        if self.vision_tower is None or images is None or input_ids.shape[1] == 1:       # :155-175
+            return input_ids, position_ids, attention_mask, past_key_values, None, labels
+        if isinstance(images, (list, tuple)) or images.ndim == 5:                          # :177-181
+            images = torch.cat([im for im in images], dim=0)
+        image_features = self.encode_images(images)                                        # [N, 256, H]
+        assert audios is not None, "the reference subscripts audio_features unconditionally (vita_arch.py:232-236)"
+        audio_out = self.encode_audios(audios["audios"], audios["lengths"])                # :186-189
+        audio_features = audio_out["inputs_embeds"]
+        ids = input_ids.tolist() if torch.is_tensor(input_ids) else [list(r) for r in input_ids]
+        if attention_mask is not None:                                                     # :213-216
+            am = attention_mask.bool().tolist()
+            ids = [[t for t, m in zip(row, mrow) if m] for row, mrow in zip(ids, am)]
+        H = self.config.llm.hidden_size
+        plan = plan_splice(ids, image_features.shape[0], image_features.shape[1], audio_features.shape[0],
+                           audio_features.shape[1], self.config.llm.tokenizer_model_max_length)
+        B, S = len(ids), plan.max_len
+        out = torch.zeros(B * S, H, dtype=BF16, device=self.device)
+        dev = self.device
+
+        def idx(v):
+            return torch.tensor(v, dtype=torch.int32).to(dev, non_blocking=True)
+
+        if plan.text_src:
+            ops.row_copy(self.packed["llm"]["embed"], idx(plan.text_src), idx(plan.text_dst), out, len(plan.text_src))
+        if plan.img_src:
+            ops.row_copy(image_features.view(-1, H), idx(plan.img_src), idx(plan.img_dst), out, len(plan.img_src))
+        if plan.aud_src:
+            ops.row_copy(audio_features.reshape(-1, H), idx(plan.aud_src), idx(plan.aud_dst), out, len(plan.aud_src))
+        inputs_embeds = out.view(B, S, H)
+        lens = torch.tensor(plan.lengths)
+        new_mask = None
+        if attention_mask is not None:
+            new_mask = (torch.arange(S)[None, :] < lens[:, None]).to(attention_mask.dtype).to(dev)
+        new_pos = None
+        if position_ids is not None:
+            new_pos = (torch.arange(S)[None, :] * (torch.arange(S)[None, :] < lens[:, None])).to(dev)
+        self._last_lengths = plan.lengths
+        return None, new_pos, new_mask, past_key_values, inputs_embeds, labels
+
+    # -- forward / generate ----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _embeds_for(self, input_ids, images, audios):
+        if images is None or input_ids.shape[1] == 1:
+            ids = input_ids.to(torch.int32).reshape(-1).to(self.device)
+            out = torch.empty(ids.numel(), self.config.llm.hidden_size, dtype=BF16, device=self.device)
+            ops.row_copy(self.packed["llm"]["embed"], ids, None, out, ids.numel())
+            return out.view(*input_ids.shape, -1), [input_ids.shape[1]] * input_ids.shape[0]
+        emb = self.prepare_inputs_labels_for_multimodal(input_ids, None, None, None, None, images, audios)[4]
+        return emb, self._last_lengths
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, labels=None, use_cache=None, images=None, audios=None, **kw) -> CausalLMOutput:
+        """vita_mixtral.py:249-289.  Prefill (any length) computes logits on all positions like the reference
+        (`custom_forward` :171-173); a single-token call with `past_key_values` set runs one decode step on the
+        paged cache owned by this object (the returned `past_key_values` is an opaque handle to it)."""
+        assert labels is None, "training is out of scope"
+        if inputs_embeds is None and input_ids is not None and input_ids.shape[1] == 1 and past_key_values is not None:
+            B = input_ids.shape[0]
+            # teacher-forceable decode step: feed the given token (not necessarily the arg-max)
+            packed = (0xFFFFFFFF - input_ids.reshape(-1).to(torch.int64)).to(self.device)
+            self.llm.best[:B].copy_(packed)
+            self.llm.decode_step(B, use_graph=False, want_logits=True)
+            return CausalLMOutput(self.llm.d_logits[:B].clone().unsqueeze(1), past_key_values)
+        if inputs_embeds is None:
+            inputs_embeds, lens = self._embeds_for(input_ids, images, audios)
+        else:
+            inputs_embeds = inputs_embeds.to(device=self.device, dtype=BF16)
+            lens = [inputs_embeds.shape[1]] * inputs_embeds.shape[0]
+        B, S, _ = inputs_embeds.shape
+        assert B <= self.llm.max_batch
+        self.llm.reset()
+        rows = []
+        for b in range(B):
+            lg = self.llm.prefill(inputs_embeds[b, : lens[b]].contiguous(), slot=b, all_logits=True)
+            if lens[b] < S:   # right padding (vita_arch.py:372-392): padded rows carry no information
+                lg = torch.cat([lg, torch.zeros(S - lens[b], lg.shape[1], dtype=lg.dtype, device=lg.device)])
+            rows.append(lg)
+        return CausalLMOutput(torch.stack(rows), "vita_b200-paged-kv")
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def generate(self, input_ids, images=None, audios=None, do_sample=False, temperature=None, top_p=None,
+                 num_beams=1, output_scores=False, return_dict_in_generate=True, max_new_tokens=16, use_cache=True,
+                 stopping_criteria=None, eos_token_id: Optional[int] = None, use_graph: bool = True, sync_every: int = 16,
+                 **kw):
+        """Greedy decode with the call signature of video_audio_demo.py:257-270.  `sequences` echoes the prompt ids
+        (placeholders included) followed by the new tokens (video_audio_demo.py:272-276)."""
+        assert not do_sample and num_beams == 1, "the hot path is greedy decode (do_sample=False, num_beams=1)"
+        assert input_ids.shape[0] == 1, "generate() is single-sequence like the demo; use the batched engine for more"
+        assert max_new_tokens <= self.llm.max_new_tokens
+        emb, lens = self._embeds_for(input_ids, images, audios)
+        self.llm.reset()
+        first = self.llm.prefill(emb[0, : lens[0]].contiguous(), slot=0, want_last_logits=output_scores)
+        new_tokens: List[int] = []
+        scores = [first.clone()] if output_scores else []   # scores[i] are the logits token i was chosen from
+        done = False
+        step = 0
+        while step < max_new_tokens and not done:
+            n = min(sync_every, max_new_tokens - step)
+            for _ in range(n):
+                self.llm.decode_step(1, use_graph=use_graph and not output_scores, want_logits=output_scores)
+                if output_scores:
+                    scores.append(self.llm.d_logits[:1].clone())
+            step += n
+            toks = self.llm.generated_tokens(0)           # one host sync per `sync_every` tokens
+            new_tokens = toks[:max_new_tokens]
+            for i, t in enumerate(new_tokens):
+                stop = (eos_token_id is not None and t == eos_token_id)
+                if not stop and stopping_criteria:
+                    seq = torch.tensor([input_ids[0].tolist() + new_tokens[: i + 1]])
+                    stop = any(bool(sc(seq, None)) for sc in stopping_criteria)
+                if stop:
+                    new_tokens = new_tokens[: i + 1]
+                    done = True
+                    break
+        seq = torch.tensor([input_ids[0].tolist() + new_tokens], dtype=torch.long)
+        if not return_dict_in_generate:
+            return seq
+        return GenerateOutput(seq, tuple(scores[: len(new_tokens)]) if output_scores else None)
