@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- VITA omni forward path on B200: 1 image + 10 s audio + text prefill -> 256-token greedy decode,
+Mixtral-8x7B geometry (32 layers, bf16, random-init weights, synthetic inputs).
+
+    python bench.py --gpus 1 --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps K ...    # the reference algorithm on the host CPU (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...          # N independent replicas (request parallel, weak scaling)
+
+A step = one complete generate(): InternViT + Whale encoders, splice, 32-layer sparse-MoE prefill, 256 decode steps.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+from vita_b200.config import VitaConfig, IMAGE_TOKEN_INDEX, AUDIO_TOKEN_INDEX  # noqa: E402
+
+METRIC = "omni_generated_tokens_per_s"
+UNIT = "tokens/s"
+TEXT_TOKENS = 128
+AUDIO_FRAMES = 998            # 10 s of 10 ms fbank frames: 1 + (160000 - 400) // 160
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def prefill_flops(S: int, cfg) -> float:
+    """Algorithmic FLOPs of the Mixtral prefill: GEMMs + causal attention + last-row lm_head."""
+    c = cfg.llm
+    H, I, L, D = c.hidden_size, c.intermediate_size, c.num_hidden_layers, c.head_dim
+    per_tok_layer = 2 * H * (c.qkv_rows) + 2 * H * c.num_attention_heads * D + 2 * H * c.num_local_experts \
+        + c.num_experts_per_tok * 3 * 2 * H * I
+    attn = 2 * S * S * c.num_attention_heads * D * L   # QK^T + PV, causal-halved
+    return per_tok_layer * L * S + attn + 2 * H * c.vocab_size
+
+
+def decode_bytes(ctx: int, cfg) -> float:
+    """Algorithmic HBM bytes of one bs=1 decode step."""
+    c = cfg.llm
+    H, I, L, D = c.hidden_size, c.intermediate_size, c.num_hidden_layers, c.head_dim
+    per_layer = (c.qkv_rows * H + H * c.num_attention_heads * D) * 2 + c.num_local_experts * H * 2 \
+        + c.num_experts_per_tok * 3 * H * I * 2 + 2 * H * 2
+    kv = 2 * c.num_key_value_heads * D * 2 * ctx
+    return L * (per_layer + kv) + c.vocab_size * H * 2 + H * 2
+
+
+def encoder_flops(cfg) -> float:
+    return 0.723e12 + 17.2e9 + 0.276e12   # InternViT tile + projector + Whale 10 s
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(cfg, seed=0, pin=True):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, cfg.llm.vocab_size, (1, TEXT_TOKENS), generator=g)
+    ids[0, 1] = IMAGE_TOKEN_INDEX
+    ids[0, 2] = AUDIO_TOKEN_INDEX
+    images = torch.randn(1, 3, cfg.vision.image_size, cfg.vision.image_size, generator=g)
+    feats = torch.randn(1, AUDIO_FRAMES, cfg.audio.input_dim, generator=g)
+    lengths = torch.tensor([AUDIO_FRAMES])
+    if pin and torch.cuda.is_available():
+        images, feats = images.pin_memory(), feats.pin_memory()
+    return ids, images, feats, lengths
+
+
+def spliced_len(cfg) -> int:
+    t2 = cfg.audio.frames_after_subsampling(AUDIO_FRAMES)
+    return TEXT_TOKENS - 2 + cfg.vision.out_tokens + cfg.audio.tokens_after_adapter(t2)
+
+
+# ================================================================================================ CPU arm (oracle port)
+def cpu_reference_sample(cfg_full, layers_cpu: int, n_decode: int, threads: int):
+    """Times the oracle (CPU restatement of the reference forward) on a bounded sample of the bench workload:
+    full-size InternViT + Whale + projector, Mixtral at full layer width but `layers_cpu` layers, the same S-token
+    spliced prompt, `n_decode` greedy steps; extrapolates the layer stack x(32 / layers_cpu)."""
+    from oracle import vita_oracle as O
+    from vita_b200 import weights as W
+    torch.set_num_threads(threads)
+    cfg = VitaConfig.full(num_hidden_layers=layers_cpu)
+    shapes = W.all_param_shapes(cfg)
+    g = torch.Generator().manual_seed(0)
+    state = {}
+    for name, shape in shapes.items():   # timing only: values need not match the GPU arm's
+        if "global_cmvn" in name:
+            state[name] = torch.zeros(shape) if name.endswith("mean") else torch.ones(shape)
+        elif len(shape) == 1 and ("norm" in name or "bn2" in name or "embed.1" in name) and name.endswith("weight"):
+            state[name] = torch.ones(shape, dtype=torch.bfloat16)
+        elif name.endswith(("ls1", "ls2")):
+            state[name] = torch.full(shape, 0.5, dtype=torch.bfloat16)
+        else:
+            state[name] = torch.empty(shape, dtype=torch.bfloat16).normal_(0.0, 0.02, generator=g)
+    state = {k: v.float() for k, v in state.items()}   # fp32 resident, as the reference's own fp32 CPU run would be
+    ids, images, feats, lengths = make_inputs(cfg, pin=False)
+    audios = {"audios": feats, "lengths": lengths}
+    t0 = time.perf_counter()
+    img_f = O.encode_images(state, cfg, images)
+    aud_f = O.encode_audios(state, cfg, feats, lengths)["inputs_embeds"]
+    emb, lens = O.prepare_inputs_embeds(state, cfg, ids, images, audios, img_f, aud_f)
+    t_enc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    logits, past, _ = O.mixtral_forward(state, cfg.llm, emb, last_only=True)
+    t_prefill = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(n_decode):
+        nxt = logits[0, -1].argmax().view(1, 1)
+        logits, past, _ = O.forward(state, cfg, nxt, past=past, last_only=True)
+    t_dec = (time.perf_counter() - t0) / max(n_decode, 1)
+    # lm_head / embedding cost is inside both measurements once; the layer stack scales with depth
+    t0 = time.perf_counter()
+    O.linear(torch.zeros(1, cfg.llm.hidden_size), state["lm_head.weight"])
+    t_head = time.perf_counter() - t0
+    scale = cfg_full.llm.num_hidden_layers / layers_cpu
+    return dict(S=lens[0], t_enc=t_enc, t_prefill=t_prefill, t_dec=t_dec, t_head=t_head,
+                t_prefill_full=(t_prefill - t_head) * scale + t_head, t_dec_full=(t_dec - t_head) * scale + t_head)
+
+
+def cpu_tokens_per_s(sample, new_tokens):
+    total = sample["t_enc"] + sample["t_prefill_full"] + new_tokens * sample["t_dec_full"]
+    return new_tokens / total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = VitaConfig.full(args.layers)
+    threads = os.cpu_count() or 1
+    vals, t_all0 = [], time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        s = cpu_reference_sample(cfg, args.cpu_layers, args.cpu_decode_tokens, threads) if i == 0 or args.cpu_repeat \
+            else s
+        if i >= args.warmup:
+            vals.append(cpu_tokens_per_s(s, args.new_tokens))
+    v = sum(vals) / len(vals)
+    sample = (f"oracle port (fp32, torch CPU, {threads} threads): full InternViT+Whale+projector, Mixtral full width x "
+              f"{args.cpu_layers} layer(s), S={s['S']} prompt, {args.cpu_decode_tokens} decode steps; layer stack "
+              f"extrapolated x{cfg.llm.num_hidden_layers // args.cpu_layers}: enc {s['t_enc']:.2f}s, prefill "
+              f"{s['t_prefill_full']:.2f}s, decode {s['t_dec_full'] * 1e3:.1f} ms/token")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * args.new_tokens / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, args, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_all0}
+    print(json.dumps(line))
+
+
+def workload_config(cfg, args, n):
+    return {"workload": "configs[2]: 1 image (448x448, 1 tile) + 10 s audio (998 fbank frames) + 126 text tokens -> "
+                        f"S={spliced_len(cfg)} omni prefill -> {args.new_tokens}-token greedy decode, bs=1 per GPU",
+            "model": f"Mixtral-8x7B geometry ({cfg.llm.num_hidden_layers} layers, H=4096, I=14336, 8 experts top-2, "
+                     "V=51760) + InternViT-300M + Whale, random init",
+            "parallelism": f"replica x{n} (request parallel; the model fits one 180 GB B200)",
+            "l2_policy": "inputs larger than L2 (93.7 GB of weights streamed every step)"}
+
+
+# ================================================================================================ GPU arm
+def run_b200(args):
+    import torch.distributed as dist
+    from vita_b200 import ops, weights as W
+    from vita_b200.model.vita_mixtral import VITAMixtralForCausalLM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = VitaConfig.full(args.layers)
+    NT = args.new_tokens
+    packed = W.random_packed(cfg, dev, seed=rank)
+    model = VITAMixtralForCausalLM(cfg, packed, dev, max_batch=1, max_seq_len=spliced_len(cfg) + NT + 64,
+                                   max_new_tokens=NT + 16)
+    ids, images_h, feats_h, lengths = make_inputs(cfg, seed=rank)
+    images_d, feats_d = images_h.to(dev), feats_h.to(dev)
+    S = spliced_len(cfg)
+    llm = model.llm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def device_step():
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        emb, lens = model._embeds_for(ids, images_d, {"audios": feats_d, "lengths": lengths})
+        e[1].record()
+        llm.reset()
+        llm.prefill(emb[0, : lens[0]].contiguous(), slot=0)
+        e[2].record()
+        for _ in range(NT):
+            llm.decode_step(1, use_graph=True)
+        e[3].record()
+        return e, lens[0]
+
+    def e2e_step():
+        return model.generate(ids, images=images_h, audios={"audios": feats_h, "lengths": lengths},
+                              max_new_tokens=NT, sync_every=NT)
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+        torch.cuda.synchronize()
+    e2e_step()
+
+    # ---- timed region: K device-resident steps --------------------------------------------------------------
+    barrier()
+    ops.launch_count(reset=True)
+    with ClockSampler(local) as clk:
+        t_all = [ev(), ev()]
+        t_all[0].record()
+        marks = [device_step() for _ in range(args.steps)]
+        t_all[1].record()
+        torch.cuda.synchronize()
+    barrier()
+    eager_launches = ops.launch_count(reset=True)
+    total_ms = t_all[0].elapsed_time(t_all[1])
+    enc_ms = sum(m[0][0].elapsed_time(m[0][1]) for m in marks) / args.steps
+    pre_ms = sum(m[0][1].elapsed_time(m[0][2]) for m in marks) / args.steps
+    dec_ms = sum(m[0][2].elapsed_time(m[0][3]) for m in marks) / args.steps
+    assert marks[0][1] == S
+    launches = eager_launches + args.steps * NT * llm.launches_per_decode_step
+    toks = llm.generated_tokens(0)
+    assert len(toks) == NT and all(0 <= t < cfg.llm.vocab_size for t in toks)
+
+    # ---- e2e: the public generate() with HOST inputs (pinned), H2D + D2H inside the timed region ------------
+    barrier()
+    t0 = [ev(), ev()]
+    t0[0].record()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = e2e_step()
+    t0[1].record()
+    torch.cuda.synchronize()
+    e2e_wall = time.perf_counter() - w0
+    e2e_ms = max(t0[0].elapsed_time(t0[1]), e2e_wall * 1e3) / args.steps
+    assert out.sequences.shape[1] == TEXT_TOKENS + NT
+    barrier()
+
+    # ---- dominant kernel, timed live with CUDA events on the launching stream (eager, outside the graph) ----
+    lw = packed["llm"]["layers"]
+    reps, gu_ms = 3, 0.0
+    for r in range(reps + 1):
+        for li in range(len(lw)):
+            a, b = ev(), ev()
+            a.record()
+            ops.decode_moe_gate_up(llm.d_h[:1], lw[li]["ln2"], lw[li]["gate"], lw[li]["w13"], llm.d_ids[:1], llm.d_w[:1],
+                                   llm.d_act[:1], cfg.llm.rms_norm_eps)
+            b.record()
+            b.synchronize()
+            if r > 0:
+                gu_ms += a.elapsed_time(b)
+    gu_ms /= reps * len(lw)
+    c = cfg.llm
+    gu_bytes = c.num_experts_per_tok * 2 * c.intermediate_size * c.hidden_size * 2 + c.hidden_size * 2 \
+        + c.num_experts_per_tok * c.intermediate_size * 2
+    pk = peaks()
+
+    # ---- reduce over ranks (max time) -----------------------------------------------------------------------
+    def rmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    total_ms, enc_ms, pre_ms, dec_ms, e2e_ms = map(rmax, (total_ms, enc_ms, pre_ms, dec_ms, e2e_ms))
+    step_ms = total_ms / args.steps
+    if rank == 0:
+        ctx_mid = S + NT // 2
+        dec_tok_s = NT / (dec_ms / 1e3)
+        line = {
+            "metric": METRIC, "value": world * NT / (step_ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(cfg, args, world),
+            "phases_ms": {"encoders_and_splice": enc_ms, "mixtral_prefill": pre_ms, "decode_total": dec_ms,
+                          "decode_per_token": dec_ms / NT},
+            "decode": {"tokens_per_s_per_gpu": dec_tok_s, "algorithmic_gb_per_token": decode_bytes(ctx_mid, cfg) / 1e9,
+                       "hbm_gbs": decode_bytes(ctx_mid, cfg) / 1e9 * dec_tok_s, "hbm_frac": decode_bytes(ctx_mid, cfg)
+                       / 1e9 * dec_tok_s / pk["hbm_gbs"]},
+            "prefill": {"S": S, "tflops": prefill_flops(S, cfg) / (pre_ms / 1e3) / 1e12,
+                        "tensor_frac": prefill_flops(S, cfg) / (pre_ms / 1e3) / 1e12 / pk["tflops"],
+                        "encoders_tflops": encoder_flops(cfg) / (enc_ms / 1e3) / 1e12},
+            "roofline": {"kernel": "stream_gemv_kernel<GateUpOp> (decode: fused RMSNorm + router + the 2 selected "
+                                   "experts' gate/up rows + SiLU*up)", "bound": "hbm", "achieved": gu_bytes / 1e9 / (gu_ms / 1e3),
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gu_bytes / 1e9 / (gu_ms / 1e3) / pk["hbm_gbs"],
+                         "traffic": None, "bytes_per_launch": gu_bytes, "us_per_launch": gu_ms * 1e3,
+                         "peak_source": pk["source"]},
+            "e2e": {"value": world * NT / (e2e_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": images_h.numel() * 4 + feats_h.numel() * 4 + ids.numel() * 8,
+                    "d2h_bytes_per_step": NT * 4, "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            s = cpu_reference_sample(cfg, args.cpu_layers, args.cpu_decode_tokens, threads)
+            line["cpu_baseline"] = {
+                "value": cpu_tokens_per_s(s, NT), "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"oracle port fp32: encoders full size, Mixtral full width x{args.cpu_layers} layer(s) "
+                          f"(stack extrapolated to {cfg.llm.num_hidden_layers}), S={s['S']}, {args.cpu_decode_tokens} "
+                          f"decode steps: enc {s['t_enc']:.2f}s prefill {s['t_prefill_full']:.2f}s decode "
+                          f"{s['t_dec_full'] * 1e3:.1f} ms/token"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--new-tokens", type=int, default=256)
+    ap.add_argument("--cpu-layers", type=int, default=1)
+    ap.add_argument("--cpu-decode-tokens", type=int, default=4)
+    ap.add_argument("--cpu-repeat", action="store_true", help="re-measure the CPU sample every step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,12 +142,15 @@ int vita_decode_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, c
                          int64_t page_size, int64_t max_pages, float eps, void* stream);
 /* h += x . W^T (o_proj + residual). */
 int vita_decode_oproj(const void* x, const void* w, void* h, int64_t B, int64_t N, int64_t K, void* stream);
-/* post_attention_layernorm + router (top-2 of 8). */
+/* post_attention_layernorm + router (top-2 of 8) as a stand-alone kernel (the decode step uses the fused form below). */
 int vita_decode_router(const void* h, const void* norm_w, const void* gate_w, void* xn, int32_t* topk_ids,
                        float* topk_w, int64_t B, int64_t H, int64_t E, float eps, void* stream);
-/* the two selected experts: act[b,k,:] = silu(gate) * up ; h[b] += sum_k w_k * down_k(act[b,k]). */
-int vita_decode_moe_gate_up(const void* xn, const void* w13, const int32_t* topk_ids, void* act, int64_t B, int64_t H,
-                            int64_t I, void* stream);
+/* post_attention_layernorm + router (fused, recomputed per CTA) + the two selected experts' gate/up rows:
+ * act[b,k,:] = silu(gate) * up; also writes topk_ids / topk_w [B,2] for the down kernel.
+ * vita_decode_moe_down: h[b] += sum_k w_k * down_k(act[b,k]). */
+int vita_decode_moe_gate_up(const void* h, const void* norm_w, const void* gate_w, const void* w13, int32_t* topk_ids,
+                            float* topk_w, void* act, int64_t B, int64_t H, int64_t I, int64_t E, float eps,
+                            void* stream);
 int vita_decode_moe_down(const void* act, const void* w2, const int32_t* topk_ids, const float* topk_w, void* h,
                          int64_t B, int64_t H, int64_t I, void* stream);
 /* final RMSNorm + lm_head on one row per sequence + arg-max on the bf16 logits (vita_mixtral.py:171-173 and the

@@ -249,9 +249,12 @@ def expert_weights(state, lcfg, l, e):
     return state[p + "w1.weight"], state[p + "w3.weight"], state[p + "w2.weight"]
 
 
-def sparse_moe(state, lcfg, l, xn):
+def sparse_moe(state, lcfg, l, xn, trace=None):
     """MixtralSparseMoeBlock / MixtralExperts.forward, modeling_mixtral.py:74-98,127-136; xn [T, H]."""
-    _, top_v, top_i = router_topk(xn, state[f"model.layers.{l}.block_sparse_moe.gate.weight"], lcfg.num_experts_per_tok)
+    probs, top_v, top_i = router_topk(xn, state[f"model.layers.{l}.block_sparse_moe.gate.weight"],
+                                      lcfg.num_experts_per_tok)
+    if trace is not None:
+        trace["router_probs"] = probs
     out = torch.zeros_like(xn)
     for e in range(lcfg.num_local_experts):
         tok, kpos = torch.where(top_i == e)
@@ -265,7 +268,7 @@ def sparse_moe(state, lcfg, l, xn):
     return out, top_i, top_v
 
 
-def decoder_layer(state, lcfg, l, h, positions, past_kv=None):
+def decoder_layer(state, lcfg, l, h, positions, past_kv=None, trace=None):
     """MixtralDecoderLayer.forward :365-390 + MixtralAttention.forward :312-351 (eager/sdpa causal GQA).
 
     h [B, S, H]; positions [B, S]; past_kv = (k, v) each [B, n_kv, P, D] or None.  Returns (h, (k, v))."""
@@ -292,12 +295,16 @@ def decoder_layer(state, lcfg, l, h, positions, past_kv=None):
     o = torch.matmul(attn, vv).transpose(1, 2).reshape(B, S, nq * D)
     h = h + linear(o, state[p + "self_attn.o_proj.weight"])                                         # :378-380
     xn = rmsnorm(h, state[p + "post_attention_layernorm.weight"], lcfg.rms_norm_eps)
-    y, _, _ = sparse_moe(state, lcfg, l, xn.reshape(-1, H))
+    if trace is not None:
+        trace["h_mid"] = h
+    y, _, _ = sparse_moe(state, lcfg, l, xn.reshape(-1, H), trace)
     return h + y.reshape(B, S, H), (k, v)                                                           # :386-389
 
 
-def mixtral_forward(state, lcfg, inputs_embeds, positions=None, past=None, last_only=False):
-    """custom_forward (vita/model/language_model/vita_mixtral.py:101-215): self.model(...) then lm_head on all rows."""
+def mixtral_forward(state, lcfg, inputs_embeds, positions=None, past=None, last_only=False, trace=None):
+    """custom_forward (vita/model/language_model/vita_mixtral.py:101-215): self.model(...) then lm_head on all rows.
+
+    `trace` (a list) collects per-layer {h_in, h_mid, router_probs, h_out} for the layer-wise parity tests."""
     B, S, _ = inputs_embeds.shape
     past_len = 0 if past is None else past[0][0].shape[2]
     if positions is None:
@@ -305,7 +312,13 @@ def mixtral_forward(state, lcfg, inputs_embeds, positions=None, past=None, last_
     h = _f(inputs_embeds)
     new_past = []
     for l in range(lcfg.num_hidden_layers):
-        h, kv = decoder_layer(state, lcfg, l, h, positions, None if past is None else past[l])
+        t = None
+        if trace is not None:
+            t = {"h_in": h}
+            trace.append(t)
+        h, kv = decoder_layer(state, lcfg, l, h, positions, None if past is None else past[l], t)
+        if t is not None:
+            t["h_out"] = h
         new_past.append(kv)
     h = rmsnorm(h, state["model.norm.weight"], lcfg.rms_norm_eps)
     if last_only:

@@ -67,14 +67,19 @@ def test_decode_moe(H, I):
     xn = torch.empty(B, H, dtype=BF16, device="cuda")
     ids = torch.empty(B, 2, dtype=torch.int32, device="cuda")
     tw = torch.empty(B, 2, dtype=torch.float32, device="cuda")
-    ops.decode_router(hd, to_dev(nw), to_dev(gw), xn, ids, tw, 1e-5)
+    ops.decode_router(hd, to_dev(nw), to_dev(gw), xn, ids, tw, 1e-5)      # stand-alone router kernel
     ref_xn = bf16_round(O.rmsnorm(h, nw, 1e-5))
     assert_close(xn, ref_xn, rel=8e-3, what="decode xn")
     _, top_v, top_i = O.router_topk(ref_xn, gw)
     assert torch.equal(ids.cpu().long(), top_i), "router ids (random logits have wide margins at this scale)"
     assert (tw.cpu() - top_v).abs().max() < 5e-3
     act = torch.empty(B, 2, I, dtype=BF16, device="cuda")
-    ops.decode_moe_gate_up(xn, w13, ids, act)
+    ids2 = torch.full((B, 2), -1, dtype=torch.int32, device="cuda")
+    tw2 = torch.zeros(B, 2, dtype=torch.float32, device="cuda")
+    ops.decode_moe_gate_up(hd, to_dev(nw), to_dev(gw), w13, ids2, tw2, act, 1e-5)   # router fused into the GEMV
+    assert torch.equal(ids2.cpu().long(), top_i)
+    assert (tw2.cpu() - top_v).abs().max() < 5e-3
+    ids, tw = ids2, tw2
     ops.decode_moe_down(act, w2, ids, tw, hd)
     want = h.clone()
     for b in range(B):

@@ -45,7 +45,7 @@ SIGNATURES = {
     "vita_decode_qkv_rope": (c_int, [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, P]),
     "vita_decode_oproj": (c_int, [P, P, P, I64, I64, I64, P]),
     "vita_decode_router": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_float, P]),
-    "vita_decode_moe_gate_up": (c_int, [P, P, P, P, I64, I64, I64, P]),
+    "vita_decode_moe_gate_up": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
     "vita_decode_moe_down": (c_int, [P, P, P, P, P, I64, I64, I64, P]),
     "vita_lm_head_argmax": (c_int, [P, I64, P, P, P, P, I64, I64, I64, c_float, P]),
 }

@@ -305,26 +305,32 @@ decode_attn_kernel(const DecodeAttnParams p) {
         for (int i = 0; i < 16; ++i) acc[h][i] = 0.0f;
     }
     const int* bt = p.block_table + static_cast<long long>(b) * p.max_pages;
-    for (int key0 = k_begin; key0 < k_end; key0 += 16) {  // trip count is uniform across the warp (shuffles below)
-        const int key = key0 + lg;
-        const bool valid = key < k_end;
-        float kf[16], vf[16];
-        if (valid) {
+    // software pipeline: the K/V rows of the next key are in flight while the current one is reduced
+    uint4 nk0, nk1, nv0, nv1;
+    auto issue = [&](int key) {
+        if (key < k_end) {
             const int page = bt[key / p.page_size];
             const long long slot = static_cast<long long>(page) * p.page_size + key % p.page_size;
             const uint4* kp = reinterpret_cast<const uint4*>(p.k_cache + (slot * p.n_kv + kvh) * DEC_D + d0);
             const uint4* vp = reinterpret_cast<const uint4*>(p.v_cache + (slot * p.n_kv + kvh) * DEC_D + d0);
-            const uint4 ka = kp[0], kc = kp[1], va = vp[0], vc = vp[1];
-            const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kc.x, kc.y, kc.z, kc.w};
-            const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vc.x, vc.y, vc.z, vc.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                kf[2 * i] = bf16_lo(kw[i]); kf[2 * i + 1] = bf16_hi(kw[i]);
-                vf[2 * i] = bf16_lo(vw[i]); vf[2 * i + 1] = bf16_hi(vw[i]);
-            }
+            nk0 = kp[0]; nk1 = kp[1]; nv0 = vp[0]; nv1 = vp[1];
         } else {
+            nk0 = nk1 = nv0 = nv1 = make_uint4(0, 0, 0, 0);
+        }
+    };
+    issue(k_begin + lg);
+    for (int key0 = k_begin; key0 < k_end; key0 += 16) {  // trip count is uniform across the warp (shuffles below)
+        const int key = key0 + lg;
+        const bool valid = key < k_end;
+        const uint4 ka = nk0, kc = nk1, va = nv0, vc = nv1;
+        issue(key + 16);
+        const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kc.x, kc.y, kc.z, kc.w};
+        const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vc.x, vc.y, vc.z, vc.w};
+        float kf[16], vf[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { kf[i] = 0.0f; vf[i] = 0.0f; }
+        for (int i = 0; i < 8; ++i) {
+            kf[2 * i] = bf16_lo(kw[i]); kf[2 * i + 1] = bf16_hi(kw[i]);
+            vf[2 * i] = bf16_lo(vw[i]); vf[2 * i + 1] = bf16_hi(vw[i]);
         }
 #pragma unroll
         for (int h = 0; h < DEC_GROUP; ++h) {
@@ -385,17 +391,29 @@ decode_attn_kernel(const DecodeAttnParams p) {
     if (!s_last) return;
     __threadfence();
     const long long sbase = (static_cast<long long>(b) * p.n_kv + kvh) * p.splits * DEC_GROUP;
+    constexpr int MAXS = 32;   // splits <= 32 (checked on the host); all loads of a head are issued before use
 #pragma unroll
     for (int h = 0; h < DEC_GROUP; ++h) {
+        float ms[MAXS], ls[MAXS], os[MAXS];
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+            if (s < p.splits) {
+                ms[s] = __ldcg(&p.part_ml[(sbase + s * DEC_GROUP + h) * 2]);
+                ls[s] = __ldcg(&p.part_ml[(sbase + s * DEC_GROUP + h) * 2 + 1]);
+                os[s] = __ldcg(&p.part_o[(sbase + s * DEC_GROUP + h) * DEC_D + d]);
+            } else {
+                ms[s] = -INFINITY; ls[s] = 0.0f; os[s] = 0.0f;
+            }
+        }
         float mm = -INFINITY;
-        for (int s = 0; s < p.splits; ++s) mm = fmaxf(mm, __ldcg(&p.part_ml[(sbase + s * DEC_GROUP + h) * 2]));
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) mm = fmaxf(mm, ms[s]);
         float ll = 0.0f, oo = 0.0f;
-        for (int s = 0; s < p.splits; ++s) {
-            const float ms = __ldcg(&p.part_ml[(sbase + s * DEC_GROUP + h) * 2]);
-            if (ms == -INFINITY) continue;
-            const float w = exp2f(ms - mm);
-            ll += w * __ldcg(&p.part_ml[(sbase + s * DEC_GROUP + h) * 2 + 1]);
-            oo += w * __ldcg(&p.part_o[(sbase + s * DEC_GROUP + h) * DEC_D + d]);
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+            const float w = (ms[s] == -INFINITY) ? 0.0f : exp2f(ms[s] - mm);
+            ll += w * ls[s];
+            oo += w * os[s];
         }
         p.out[(static_cast<long long>(b) * p.n_q + kvh * DEC_GROUP + h) * DEC_D + d] =
             __float2bfloat16(ll > 0.0f ? oo / ll : 0.0f);
@@ -447,7 +465,7 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
                                      int64_t B, int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim,
                                      int64_t page_size, int64_t max_pages, int64_t splits, float scale, void* stream) {
     VITA_REQUIRE(head_dim == DEC_D && n_q_heads == n_kv_heads * DEC_GROUP, "decode attention: need D=128, GQA group 4");
-    VITA_REQUIRE(splits >= 1 && workspace != nullptr, "splits >= 1 and a workspace are required");
+    VITA_REQUIRE(splits >= 1 && splits <= 32 && workspace != nullptr, "1 <= splits <= 32 and a workspace are required");
     if (B == 0) return VITA_OK;
     DecodeAttnParams p{};
     p.q = BF16C(q); p.k_cache = BF16C(k_cache); p.v_cache = BF16C(v_cache);

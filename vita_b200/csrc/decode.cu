@@ -22,39 +22,57 @@ namespace vita {
 constexpr int GV_KC = 4096;                    // elements per row per stage
 constexpr int GV_STAGE_BYTES = 2 * GV_KC * 2;  // two rows of bf16
 constexpr int GV_STAGES = 8;
-constexpr int GV_CONSUMERS = 256;
-constexpr int GV_THREADS = GV_CONSUMERS + 32;
+constexpr int GV_GROUP_WARPS = 8;              // consumer warps per group
+constexpr int GV_CONSUMERS = 512;              // two groups of 8 warps working on alternating batches of stages
+constexpr int GV_THREADS = GV_CONSUMERS + 32;  // + producer warp
+constexpr int GV_NB = 4;                       // items per batch (one reduction + one named barrier per batch)
+constexpr int GV_PREP_FLOATS = 256;            // per-CTA epilogue constants prefetched before streaming starts
 
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void consumer_barrier_all() { asm volatile("bar.sync 3, 512;" ::: "memory"); }
+__device__ __forceinline__ void group_barrier(int group) {
+    asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+}
 
-__device__ __forceinline__ float consumer_block_sum(float v, float* red8) {
+// sum over the 512 consumer threads; scratch: >= 16 floats
+__device__ __forceinline__ float consumer_sum(float v, float* scratch) {
     v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) red8[threadIdx.x >> 5] = v;
-    consumer_barrier();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    consumer_barrier_all();
     float t = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red8[i];
-    consumer_barrier();
+    for (int i = 0; i < 16; ++i) t += scratch[i];
+    consumer_barrier_all();
     return t;
 }
 
 // xs[0..K) = bf16(rmsnorm(h) * w)   (consumer threads only)
 __device__ __forceinline__ void load_x_rmsnorm(const __nv_bfloat16* h, const __nv_bfloat16* w, __nv_bfloat16* xs, int K,
-                                               float eps, float* red8) {
+                                               float eps, float* scratch) {
     float ss = 0.0f;
-    for (int i = threadIdx.x; i < K; i += GV_CONSUMERS) {
-        const float v = __bfloat162float(h[i]);
-        ss += v * v;
+    for (int i = threadIdx.x * 8; i < K; i += GV_CONSUMERS * 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(h + i);
+        const uint32_t a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ss += bf16_lo(a[e]) * bf16_lo(a[e]) + bf16_hi(a[e]) * bf16_hi(a[e]);
     }
-    const float tot = consumer_block_sum(ss, red8);
+    const float tot = consumer_sum(ss, scratch);
     const float inv = rsqrtf(tot / static_cast<float>(K) + eps);
-    for (int i = threadIdx.x; i < K; i += GV_CONSUMERS)
-        xs[i] = __float2bfloat16(__bfloat162float(h[i]) * inv * __bfloat162float(w[i]));
+    for (int i = threadIdx.x * 8; i < K; i += GV_CONSUMERS * 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(h + i);
+        const uint4 g = __ldg(reinterpret_cast<const uint4*>(w + i));
+        const uint32_t a[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w};
+        uint4 o;
+        uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            op[e] = pack_bf16(bf16_lo(a[e]) * inv * bf16_lo(gg[e]), bf16_hi(a[e]) * inv * bf16_hi(gg[e]));
+        *reinterpret_cast<uint4*>(xs + i) = o;
+    }
 }
 __device__ __forceinline__ void load_x_copy(const __nv_bfloat16* src, __nv_bfloat16* xs, int n) {
     for (int i = threadIdx.x * 8; i < n; i += GV_CONSUMERS * 8)
@@ -66,6 +84,15 @@ struct FinishState {
     int best_idx;
 };
 
+// Shared-memory context handed to the ops.
+struct GvSmem {
+    __nv_bfloat16* xs;   // activation vector(s)
+    float* scratch;      // 64 floats
+    float* prep;         // GV_PREP_FLOATS floats of per-CTA epilogue constants
+    int* misc;           // 8 ints (e.g. selected expert ids, position, slot)
+    uint64_t* aux_bar;   // producer gate for ops whose row addresses depend on the prologue (router)
+};
+
 template <class Op>
 __global__ void __launch_bounds__(GV_THREADS, 1)
 stream_gemv_kernel(const Op op) {
@@ -75,8 +102,12 @@ stream_gemv_kernel(const Op op) {
     uint8_t* tail = reinterpret_cast<uint8_t*>(xs) + ((op.x_elems() * 2 + 127) / 128) * 128;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
     uint64_t* empty_bar = full_bar + GV_STAGES;
-    float* red = reinterpret_cast<float*>(empty_bar + GV_STAGES);  // [2][8][2] + [8] scratch
-    float* red8 = red + 32;
+    uint64_t* aux_bar = empty_bar + GV_STAGES;
+    float* red = reinterpret_cast<float*>(aux_bar + 2);   // [2 groups][2 parities][8 warps][8]
+    float* scratch = red + 2 * 2 * 8 * 8;                 // 64
+    float* prep = scratch + 64;                           // GV_PREP_FLOATS
+    int* misc = reinterpret_cast<int*>(prep + GV_PREP_FLOATS);
+    GvSmem sm{xs, scratch, prep, misc, aux_bar};
 
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,19 +120,21 @@ stream_gemv_kernel(const Op op) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < GV_STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 8);
+            mbar_init(&empty_bar[i], GV_GROUP_WARPS);
         }
+        mbar_init(aux_bar, 1);
         fence_barrier_init();
     }
     __syncthreads();
 
-    if (warp == 8) {
+    if (warp == GV_CONSUMERS / 32) {
         if (lane == 0) {
+            if (Op::kProducerNeedsPrologue) mbar_wait(aux_bar, 0, 13);
             int stage = 0;
             uint32_t phase = 0;
             for (int item = i0; item < i1; ++item) {
-                const __nv_bfloat16* r0 = op.row_ptr(b, item, 0);
-                const __nv_bfloat16* r1 = op.row_ptr(b, item, 1);
+                const __nv_bfloat16* r0 = op.row_ptr(b, item, 0, sm);
+                const __nv_bfloat16* r1 = op.row_ptr(b, item, 1, sm);
                 for (int c = 0; c < n_chunks; ++c) {
                     const int len = min(GV_KC, K - c * GV_KC);
                     mbar_wait(&empty_bar[stage], phase ^ 1, 11);
@@ -116,58 +149,91 @@ stream_gemv_kernel(const Op op) {
         return;
     }
 
-    // ---------------------------------------------------------------- consumers (256 threads)
-    op.load_x(b, xs, red8);
-    consumer_barrier();
+    // ---------------------------------------------------------------- consumers (512 threads, 2 groups of 8 warps)
+    op.prologue(b, sm, i0, i1);
+    consumer_barrier_all();
     FinishState st{-INFINITY, 0x7fffffff};
+    const int group = warp >> 3, gw = warp & 7;
+    const int NB = (n_chunks == 1) ? GV_NB : 1;
     int stage = 0;
     uint32_t phase = 0;
-    const int x1_off = op.x_per_row() ? K : 0;
-    for (int item = i0; item < i1; ++item) {
-        float a0 = 0.0f, a1 = 0.0f;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int len = min(GV_KC, K - c * GV_KC);
-            mbar_wait(&full_bar[stage], phase, 12);
-            const uint8_t* w0p = ring + stage * GV_STAGE_BYTES;
-            const uint8_t* w1p = w0p + GV_KC * 2;
+    int bi = 0;
+    for (int item0 = i0; item0 < i1; item0 += NB, ++bi) {
+        const int nb = min(NB, i1 - item0);
+        if ((bi & 1) != group) {  // the other group's batch: skip its stages
+            stage += nb * n_chunks;
+            while (stage >= GV_STAGES) { stage -= GV_STAGES; phase ^= 1; }
+            continue;
+        }
+        float acc[GV_NB][2];
 #pragma unroll
-            for (int pss = 0; pss < 2; ++pss) {
-                const int off = warp * 512 + pss * 256 + lane * 8;
-                if (off < len) {
-                    const uint4 w0 = *reinterpret_cast<const uint4*>(w0p + off * 2);
-                    const uint4 w1 = *reinterpret_cast<const uint4*>(w1p + off * 2);
-                    const uint4 x0 = *reinterpret_cast<const uint4*>(xs + c * GV_KC + off);
-                    const uint4 x1 = *reinterpret_cast<const uint4*>(xs + x1_off + c * GV_KC + off);
-                    const uint32_t a[4] = {w0.x, w0.y, w0.z, w0.w}, bb[4] = {w1.x, w1.y, w1.z, w1.w};
-                    const uint32_t xa[4] = {x0.x, x0.y, x0.z, x0.w}, xb[4] = {x1.x, x1.y, x1.z, x1.w};
+        for (int q = 0; q < GV_NB; ++q) { acc[q][0] = 0.0f; acc[q][1] = 0.0f; }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        a0 += bf16_lo(a[e]) * bf16_lo(xa[e]) + bf16_hi(a[e]) * bf16_hi(xa[e]);
-                        a1 += bf16_lo(bb[e]) * bf16_lo(xb[e]) + bf16_hi(bb[e]) * bf16_hi(xb[e]);
+        for (int q = 0; q < GV_NB; ++q) {
+            if (q < nb) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int len = min(GV_KC, K - c * GV_KC);
+                    mbar_wait(&full_bar[stage], phase, 12);
+                    const uint8_t* w0p = ring + stage * GV_STAGE_BYTES;
+                    const uint8_t* w1p = w0p + GV_KC * 2;
+#pragma unroll
+                    for (int pss = 0; pss < 2; ++pss) {
+                        const int off = gw * 512 + pss * 256 + lane * 8;
+                        if (off < len) {
+                            const uint4 w0 = *reinterpret_cast<const uint4*>(w0p + off * 2);
+                            const uint4 w1 = *reinterpret_cast<const uint4*>(w1p + off * 2);
+                            const uint4 x0 = *reinterpret_cast<const uint4*>(xs + c * GV_KC + off);
+                            const uint32_t a[4] = {w0.x, w0.y, w0.z, w0.w}, bb[4] = {w1.x, w1.y, w1.z, w1.w};
+                            const uint32_t xa[4] = {x0.x, x0.y, x0.z, x0.w};
+                            if constexpr (Op::kXPerRow) {
+                                const uint4 x1 = *reinterpret_cast<const uint4*>(xs + K + c * GV_KC + off);
+                                const uint32_t xb[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    acc[q][0] += bf16_lo(a[e]) * bf16_lo(xa[e]) + bf16_hi(a[e]) * bf16_hi(xa[e]);
+                                    acc[q][1] += bf16_lo(bb[e]) * bf16_lo(xb[e]) + bf16_hi(bb[e]) * bf16_hi(xb[e]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float xl = bf16_lo(xa[e]), xh = bf16_hi(xa[e]);
+                                    acc[q][0] += bf16_lo(a[e]) * xl + bf16_hi(a[e]) * xh;
+                                    acc[q][1] += bf16_lo(bb[e]) * xl + bf16_hi(bb[e]) * xh;
+                                }
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                    if (++stage == GV_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
-            if (++stage == GV_STAGES) { stage = 0; phase ^= 1; }
         }
-        a0 = warp_sum(a0);
-        a1 = warp_sum(a1);
-        float* rb = red + (item & 1) * 16;
-        if (lane == 0) { rb[warp * 2] = a0; rb[warp * 2 + 1] = a1; }
-        consumer_barrier();
-        if (warp == (item & 7) && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < GV_NB; ++q) {
+            acc[q][0] = warp_sum(acc[q][0]);
+            acc[q][1] = warp_sum(acc[q][1]);
+        }
+        float* rb = red + ((group * 2 + ((bi >> 1) & 1)) * 8) * 8;
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < GV_NB; ++q) { rb[gw * 8 + q * 2] = acc[q][0]; rb[gw * 8 + q * 2 + 1] = acc[q][1]; }
+        }
+        group_barrier(group);
+        if (gw < nb && lane == 0) {
             float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) { s0 += rb[w * 2]; s1 += rb[w * 2 + 1]; }
-            op.finish(b, item, s0, s1, st);
+            for (int w = 0; w < 8; ++w) { s0 += rb[w * 8 + gw * 2]; s1 += rb[w * 8 + gw * 2 + 1]; }
+            op.finish(b, item0 + gw, s0, s1, st, sm, i0);
         }
     }
-    op.finalize(b, st, red8);
+    op.finalize(b, st);
 }
 
 // ------------------------------------------------------------------------------------------------ ops
 struct QkvOp {
+    static constexpr bool kXPerRow = false;
+    static constexpr bool kProducerNeedsPrologue = false;
     const __nv_bfloat16* h;       // [B, H]
     const __nv_bfloat16* norm_w;  // [H]
     const __nv_bfloat16* w_qkv;   // [(n_q + 2 n_kv) * 128, H]
@@ -181,24 +247,28 @@ struct QkvOp {
     float eps;
 
     __device__ int x_elems() const { return K; }
-    __device__ bool x_per_row() const { return false; }
     __device__ long long num_items() const { return static_cast<long long>(n_q + 2 * n_kv) * 64; }
-    __device__ const __nv_bfloat16* row_ptr(int, int item, int r) const {
+    __device__ const __nv_bfloat16* row_ptr(int, int item, int r, const GvSmem&) const {
         const int head = item >> 6, j = item & 63;
         return w_qkv + static_cast<long long>(head * 128 + j + r * 64) * K;
     }
-    __device__ void load_x(int b, __nv_bfloat16* xs, float* red8) const {
-        load_x_rmsnorm(h + static_cast<long long>(b) * K, norm_w, xs, K, eps, red8);
-    }
-    __device__ void finish(int b, int item, float s0, float s1, FinishState&) const {
-        const int head = item >> 6, j = item & 63;
+    __device__ void prologue(int b, const GvSmem& sm, int, int) const {
+        // epilogue constants: position, cache slot, the cos/sin row of this position
         const int pos = cur_pos[b];
+        if (threadIdx.x < 128) sm.prep[threadIdx.x] = cos_sin[static_cast<long long>(pos) * 128 + threadIdx.x];
+        if (threadIdx.x == 0) {
+            const int page = block_table[static_cast<long long>(b) * max_pages + pos / page_size];
+            sm.misc[0] = page * page_size + pos % page_size;
+        }
+        load_x_rmsnorm(h + static_cast<long long>(b) * K, norm_w, sm.xs, K, eps, sm.scratch);
+    }
+    __device__ void finish(int b, int item, float s0, float s1, FinishState&, const GvSmem& sm, int) const {
+        const int head = item >> 6, j = item & 63;
         // qkv projections are rounded to bf16 before RoPE, as the GEMM path (and the reference) does
         s0 = __bfloat162float(__float2bfloat16(s0));
         s1 = __bfloat162float(__float2bfloat16(s1));
         if (head < n_q + n_kv) {
-            const float c = cos_sin[static_cast<long long>(pos) * 128 + j];
-            const float s = cos_sin[static_cast<long long>(pos) * 128 + 64 + j];
+            const float c = sm.prep[j], s = sm.prep[64 + j];
             const float o0 = s0 * c - s1 * s, o1 = s1 * c + s0 * s;
             s0 = o0;
             s1 = o1;
@@ -208,8 +278,7 @@ struct QkvOp {
             q[j] = __float2bfloat16(s0);
             q[j + 64] = __float2bfloat16(s1);
         } else {
-            const int page = block_table[static_cast<long long>(b) * max_pages + pos / page_size];
-            const long long slot = static_cast<long long>(page) * page_size + pos % page_size;
+            const long long slot = sm.misc[0];
             const bool is_k = head < n_q + n_kv;
             const int kvh = is_k ? head - n_q : head - n_q - n_kv;
             __nv_bfloat16* dst = (is_k ? k_cache : v_cache) + (slot * n_kv + kvh) * 128;
@@ -217,54 +286,154 @@ struct QkvOp {
             dst[j + 64] = __float2bfloat16(s1);
         }
     }
-    __device__ void finalize(int, FinishState&, float*) const {}
+    __device__ void finalize(int, FinishState&) const {}
 };
 
 struct OProjOp {
+    static constexpr bool kXPerRow = false;
+    static constexpr bool kProducerNeedsPrologue = false;
     const __nv_bfloat16* x;  // [B, K] attention output
     const __nv_bfloat16* w;  // [N, K]
     __nv_bfloat16* h;        // [B, N] residual stream, updated in place
     int K, N;
 
     __device__ int x_elems() const { return K; }
-    __device__ bool x_per_row() const { return false; }
     __device__ long long num_items() const { return N / 2; }
-    __device__ const __nv_bfloat16* row_ptr(int, int item, int r) const {
+    __device__ const __nv_bfloat16* row_ptr(int, int item, int r, const GvSmem&) const {
         return w + static_cast<long long>(item * 2 + r) * K;
     }
-    __device__ void load_x(int b, __nv_bfloat16* xs, float*) const { load_x_copy(x + static_cast<long long>(b) * K, xs, K); }
-    __device__ void finish(int b, int item, float s0, float s1, FinishState&) const {
-        __nv_bfloat16* hr = h + static_cast<long long>(b) * N + item * 2;
-        hr[0] = __float2bfloat16(__bfloat162float(hr[0]) + s0);
-        hr[1] = __float2bfloat16(__bfloat162float(hr[1]) + s1);
+    __device__ void prologue(int b, const GvSmem& sm, int i0, int i1) const {
+        const int n = (i1 - i0) * 2;   // residual values of this CTA's rows, prefetched so finish() never waits
+        if (n <= GV_PREP_FLOATS)
+            for (int i = threadIdx.x; i < n; i += GV_CONSUMERS)
+                sm.prep[i] = __bfloat162float(h[static_cast<long long>(b) * N + i0 * 2 + i]);
+        load_x_copy(x + static_cast<long long>(b) * K, sm.xs, K);
     }
-    __device__ void finalize(int, FinishState&, float*) const {}
+    __device__ void finish(int b, int item, float s0, float s1, FinishState&, const GvSmem& sm, int i0) const {
+        __nv_bfloat16* hr = h + static_cast<long long>(b) * N + item * 2;
+        float r0, r1;
+        if ((static_cast<int>(num_items() * (blockIdx.x + 1) / gridDim.x) - i0) * 2 <= GV_PREP_FLOATS) {
+            r0 = sm.prep[(item - i0) * 2];
+            r1 = sm.prep[(item - i0) * 2 + 1];
+        } else {
+            r0 = __bfloat162float(hr[0]);
+            r1 = __bfloat162float(hr[1]);
+        }
+        *reinterpret_cast<uint32_t*>(hr) = pack_bf16(r0 + s0, r1 + s1);
+    }
+    __device__ void finalize(int, FinishState&) const {}
 };
 
+// post_attention_layernorm + router (top-2 of 8, fp32 softmax, renormalised) fused into the expert gate/up GEMV:
+// every CTA recomputes the 8 router logits (64 KB of L2-resident gate weights) instead of paying a kernel boundary.
 struct GateUpOp {
-    const __nv_bfloat16* xn;     // [B, H] normed activations (written by the router kernel)
-    const __nv_bfloat16* w13;    // [E, 2I, H]
-    const int* topk_ids;         // [B, 2]
-    __nv_bfloat16* act;          // [B, 2, I]
+    static constexpr bool kXPerRow = false;
+    static constexpr bool kProducerNeedsPrologue = true;
+    const __nv_bfloat16* h;        // [B, H] residual stream (post attention)
+    const __nv_bfloat16* norm_w;   // [H]
+    const __nv_bfloat16* gate_w;   // [8, H]
+    const __nv_bfloat16* w13;      // [E, 2I, H]
+    int* topk_ids;                 // [B, 2]  (written by CTA 0 for the down kernel)
+    float* topk_w;                 // [B, 2]
+    __nv_bfloat16* act;            // [B, 2, I]
     int K, I;
+    float eps;
 
     __device__ int x_elems() const { return K; }
-    __device__ bool x_per_row() const { return false; }
     __device__ long long num_items() const { return 2ll * I; }
-    __device__ const __nv_bfloat16* row_ptr(int b, int item, int r) const {
+    __device__ const __nv_bfloat16* row_ptr(int, int item, int r, const GvSmem& sm) const {
         const int k = item / I, j = item % I;
-        const int e = topk_ids[b * 2 + k];
+        const int e = sm.misc[k];
         return w13 + (static_cast<long long>(e) * 2 * I + r * I + j) * K;
     }
-    __device__ void load_x(int b, __nv_bfloat16* xs, float*) const { load_x_copy(xn + static_cast<long long>(b) * K, xs, K); }
-    __device__ void finish(int b, int item, float s0, float s1, FinishState&) const {
+    __device__ void prologue(int b, const GvSmem& sm, int, int) const {
+        const __nv_bfloat16* hr = h + static_cast<long long>(b) * K;
+        float part[9];   // sum of squares + 8 un-normalised logits  sum_i (h_i * w_i) * g_ei
+#pragma unroll
+        for (int e = 0; e < 9; ++e) part[e] = 0.0f;
+        for (int i = threadIdx.x * 8; i < K; i += GV_CONSUMERS * 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(hr + i);
+            const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w + i));
+            uint4 ge[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ge[e] = __ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * K + i));
+            const uint32_t a[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w};
+            float xw[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float lo = bf16_lo(a[q]), hi = bf16_hi(a[q]);
+                part[0] += lo * lo + hi * hi;
+                xw[2 * q] = lo * bf16_lo(gg[q]);
+                xw[2 * q + 1] = hi * bf16_hi(gg[q]);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t w[4] = {ge[e].x, ge[e].y, ge[e].z, ge[e].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) part[1 + e] += xw[2 * q] * bf16_lo(w[q]) + xw[2 * q + 1] * bf16_hi(w[q]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 9; ++e) part[e] = warp_sum(part[e]);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float* red9 = sm.prep;   // [16 warps][9]
+        if (lane == 0)
+#pragma unroll
+            for (int e = 0; e < 9; ++e) red9[warp * 9 + e] = part[e];
+        consumer_barrier_all();
+        float tot[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+            tot[e] = 0.0f;
+            for (int w = 0; w < 16; ++w) tot[e] += red9[w * 9 + e];
+        }
+        const float inv = rsqrtf(tot[0] / static_cast<float>(K) + eps);
+        float p[8], m = -INFINITY, sum = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { p[e] = tot[1 + e] * inv; m = fmaxf(m, p[e]); }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { p[e] = expf(p[e] - m); sum += p[e]; }
+        int e0 = 0;
+#pragma unroll
+        for (int e = 1; e < 8; ++e) if (p[e] > p[e0]) e0 = e;
+        int e1 = (e0 == 0) ? 1 : 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (e != e0 && p[e] > p[e1]) e1 = e;
+        if (threadIdx.x == 0) {
+            sm.misc[0] = e0;
+            sm.misc[1] = e1;
+            mbar_arrive(sm.aux_bar);   // release the producer: the rows to stream are now known
+            if (blockIdx.x == 0) {
+                const float p0 = p[e0] / sum, p1 = p[e1] / sum, den = p0 + p1;
+                topk_ids[b * 2] = e0;
+                topk_ids[b * 2 + 1] = e1;
+                topk_w[b * 2] = p0 / den;
+                topk_w[b * 2 + 1] = p1 / den;
+            }
+        }
+        // normalised activations (bf16) for the GEMV
+        for (int i = threadIdx.x * 8; i < K; i += GV_CONSUMERS * 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(hr + i);
+            const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w + i));
+            const uint32_t a[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w};
+            uint4 o;
+            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                op[q] = pack_bf16(bf16_lo(a[q]) * inv * bf16_lo(gg[q]), bf16_hi(a[q]) * inv * bf16_hi(gg[q]));
+            *reinterpret_cast<uint4*>(sm.xs + i) = o;
+        }
+    }
+    __device__ void finish(int b, int item, float s0, float s1, FinishState&, const GvSmem&, int) const {
         // gate and up are bf16 linear outputs in the reference; silu(gate) * up in fp32, one rounding
         act[static_cast<long long>(b) * 2 * I + item] = __float2bfloat16(silu(s0) * s1);
     }
-    __device__ void finalize(int, FinishState&, float*) const {}
+    __device__ void finalize(int, FinishState&) const {}
 };
 
 struct DownOp {
+    static constexpr bool kXPerRow = true;
+    static constexpr bool kProducerNeedsPrologue = false;
     const __nv_bfloat16* act;   // [B, 2, I]
     const __nv_bfloat16* w2;    // [E, H, I]
     const int* topk_ids;        // [B, 2]
@@ -273,21 +442,27 @@ struct DownOp {
     int K, H;                   // K = I
 
     __device__ int x_elems() const { return 2 * K; }
-    __device__ bool x_per_row() const { return true; }
     __device__ long long num_items() const { return H; }
-    __device__ const __nv_bfloat16* row_ptr(int b, int item, int r) const {
+    __device__ const __nv_bfloat16* row_ptr(int b, int item, int r, const GvSmem&) const {
         const int e = topk_ids[b * 2 + r];
         return w2 + (static_cast<long long>(e) * H + item) * K;
     }
-    __device__ void load_x(int b, __nv_bfloat16* xs, float*) const {
-        load_x_copy(act + static_cast<long long>(b) * 2 * K, xs, 2 * K);
+    __device__ void prologue(int b, const GvSmem& sm, int i0, int i1) const {
+        const int n = i1 - i0;
+        if (n <= GV_PREP_FLOATS - 2)
+            for (int i = threadIdx.x; i < n; i += GV_CONSUMERS)
+                sm.prep[i] = __bfloat162float(h[static_cast<long long>(b) * H + i0 + i]);
+        if (threadIdx.x < 2) sm.prep[GV_PREP_FLOATS - 2 + threadIdx.x] = topk_w[b * 2 + threadIdx.x];
+        load_x_copy(act + static_cast<long long>(b) * 2 * K, sm.xs, 2 * K);
     }
-    __device__ void finish(int b, int item, float s0, float s1, FinishState&) const {
+    __device__ void finish(int b, int item, float s0, float s1, FinishState&, const GvSmem& sm, int i0) const {
         __nv_bfloat16* hr = h + static_cast<long long>(b) * H + item;
-        const float y = topk_w[b * 2] * s0 + topk_w[b * 2 + 1] * s1;
-        hr[0] = __float2bfloat16(__bfloat162float(hr[0]) + y);
+        const int n = static_cast<int>(num_items() * (blockIdx.x + 1) / gridDim.x) - i0;
+        const float r = (n <= GV_PREP_FLOATS - 2) ? sm.prep[item - i0] : __bfloat162float(hr[0]);
+        const float y = sm.prep[GV_PREP_FLOATS - 2] * s0 + sm.prep[GV_PREP_FLOATS - 1] * s1;
+        hr[0] = __float2bfloat16(r + y);
     }
-    __device__ void finalize(int, FinishState&, float*) const {}
+    __device__ void finalize(int, FinishState&) const {}
 };
 
 __device__ __forceinline__ unsigned long long pack_argmax(float v, int idx) {
@@ -297,6 +472,8 @@ __device__ __forceinline__ unsigned long long pack_argmax(float v, int idx) {
 }
 
 struct LmHeadOp {
+    static constexpr bool kXPerRow = false;
+    static constexpr bool kProducerNeedsPrologue = false;
     const __nv_bfloat16* h;        // rows of the residual stream, row b at h + b * h_stride
     long long h_stride;
     const __nv_bfloat16* norm_w;   // final RMSNorm
@@ -307,17 +484,16 @@ struct LmHeadOp {
     float eps;
 
     __device__ int x_elems() const { return K; }
-    __device__ bool x_per_row() const { return false; }
     __device__ long long num_items() const { return (V + 1) / 2; }
-    __device__ const __nv_bfloat16* row_ptr(int, int item, int r) const {
+    __device__ const __nv_bfloat16* row_ptr(int, int item, int r, const GvSmem&) const {
         int row = item * 2 + r;
         if (row >= V) row = V - 1;
         return w + static_cast<long long>(row) * K;
     }
-    __device__ void load_x(int b, __nv_bfloat16* xs, float* red8) const {
-        load_x_rmsnorm(h + static_cast<long long>(b) * h_stride, norm_w, xs, K, eps, red8);
+    __device__ void prologue(int b, const GvSmem& sm, int, int) const {
+        load_x_rmsnorm(h + static_cast<long long>(b) * h_stride, norm_w, sm.xs, K, eps, sm.scratch);
     }
-    __device__ void finish(int b, int item, float s0, float s1, FinishState& st) const {
+    __device__ void finish(int b, int item, float s0, float s1, FinishState& st, const GvSmem&, int) const {
         const int r0 = item * 2, r1 = item * 2 + 1;
         // logits stay in the activation dtype and arg-max runs on them (vita_mixtral.py:171-173)
         const __nv_bfloat16 l0 = __float2bfloat16(s0), l1 = __float2bfloat16(s1);
@@ -329,15 +505,15 @@ struct LmHeadOp {
         if (f0 > st.best || (f0 == st.best && r0 < st.best_idx)) { st.best = f0; st.best_idx = r0; }
         if (r1 < V && (f1 > st.best || (f1 == st.best && r1 < st.best_idx))) { st.best = f1; st.best_idx = r1; }
     }
-    __device__ void finalize(int b, FinishState& st, float*) const {
+    __device__ void finalize(int b, FinishState& st) const {
         if ((threadIdx.x & 31) == 0 && st.best_idx != 0x7fffffff) atomicMax(&best[b], pack_argmax(st.best, st.best_idx));
     }
 };
 
 template <class Op>
 static int launch_stream_gemv(const Op& op, int x_elems, int B, cudaStream_t st, const char* name) {
-    const int smem_bytes = GV_STAGES * GV_STAGE_BYTES + ((x_elems * 2 + 127) / 128) * 128 + 2 * GV_STAGES * 8 +
-                           (32 + 8) * 4 + 256;
+    const int smem_bytes = GV_STAGES * GV_STAGE_BYTES + ((x_elems * 2 + 127) / 128) * 128 + (2 * GV_STAGES + 2) * 8 +
+                           (2 * 2 * 8 * 8 + 64 + GV_PREP_FLOATS + 8) * 4 + 256;
     auto kern = stream_gemv_kernel<Op>;
     static int configured_bytes = 0;
     if (smem_bytes > configured_bytes) {
@@ -476,11 +652,14 @@ extern "C" int vita_decode_router(const void* h, const void* norm_w, const void*
     return check_launch("decode_router");
 }
 
-extern "C" int vita_decode_moe_gate_up(const void* xn, const void* w13, const int32_t* topk_ids, void* act, int64_t B,
-                                       int64_t H, int64_t I, void* stream) {
+extern "C" int vita_decode_moe_gate_up(const void* h, const void* norm_w, const void* gate_w, const void* w13,
+                                       int32_t* topk_ids, float* topk_w, void* act, int64_t B, int64_t H, int64_t I,
+                                       int64_t E, float eps, void* stream) {
     VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    VITA_REQUIRE(E == 8, "router is specialised for 8 experts (Mixtral-8x7B)");
     if (B == 0) return VITA_OK;
-    GateUpOp op{BF16C(xn), BF16C(w13), topk_ids, static_cast<__nv_bfloat16*>(act), (int)H, (int)I};
+    GateUpOp op{BF16C(h), BF16C(norm_w), BF16C(gate_w), BF16C(w13), topk_ids, topk_w,
+                static_cast<__nv_bfloat16*>(act), (int)H, (int)I, eps};
     return launch_stream_gemv(op, (int)H, (int)B, static_cast<cudaStream_t>(stream), "decode_moe_gate_up");
 }
 

@@ -163,20 +163,20 @@ class MixtralDecoder:
                                  self.d_attn[:B], self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits,
                                  D ** -0.5)
             ops.decode_oproj(self.d_attn[:B], lw["wo"], h)
-            ops.decode_router(h, lw["ln2"], lw["gate"], self.d_xn[:B], self.d_ids[:B], self.d_w[:B], c.rms_norm_eps)
-            ops.decode_moe_gate_up(self.d_xn[:B], lw["w13"], self.d_ids[:B], self.d_act[:B])
+            ops.decode_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B], self.d_act[:B],
+                                   c.rms_norm_eps)
             ops.decode_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h)
         ops.lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], self.d_logits[:B] if want_logits else None,
                            self.best[:B], B, c.rms_norm_eps)
 
     @property
     def launches_per_decode_step(self) -> int:
-        return 2 + 6 * self.cfg.num_hidden_layers
+        return 2 + 5 * self.cfg.num_hidden_layers
 
     @torch.no_grad()
     def decode_step(self, B: int = 1, use_graph: bool = True, want_logits: bool = False):
         """Generate one token for batch slots [0, B): consumes self.best, appends to token_log, leaves the next
-        arg-max in self.best.  With use_graph the whole step (2 + 6 * layers kernels) replays as one CUDA graph."""
+        arg-max in self.best.  With use_graph the whole step (2 + 5 * layers kernels) replays as one CUDA graph."""
         if not use_graph:
             self._decode_step_kernels(B, want_logits)
             return

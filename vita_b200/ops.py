@@ -243,9 +243,11 @@ def decode_router(h, norm_w, gate_w, xn, topk_ids, topk_w, eps):
               gate_w.shape[0], float(eps), _stream())
 
 
-def decode_moe_gate_up(xn, w13, topk_ids, act):
-    B, H = xn.shape
-    _lib.call("vita_decode_moe_gate_up", _p(xn), _p(w13), _p(topk_ids), _p(act), B, H, w13.shape[1] // 2, _stream())
+def decode_moe_gate_up(h, norm_w, gate_w, w13, topk_ids, topk_w, act, eps):
+    """Fused post-attention RMSNorm + router + selected experts' gate/up GEMV; writes topk_ids / topk_w."""
+    B, H = h.shape
+    _lib.call("vita_decode_moe_gate_up", _p(h), _p(norm_w), _p(gate_w), _p(w13), _p(topk_ids), _p(topk_w), _p(act), B, H,
+              w13.shape[1] // 2, gate_w.shape[0], float(eps), _stream())
 
 
 def decode_moe_down(act, w2, topk_ids, topk_w, h):
