@@ -219,7 +219,7 @@ def test_full_width_mixtral_two_layers_prefill_and_decode_match_oracle():
         toks.append(nxt)
         rows.append(lg[0, -1])
         tr = []
-        lg, past, _ = O.mixtral_forward(state, cfg.llm, state["model.embed_tokens.weight"].float()[[[nxt]]], past=past,
+        lg, past, _ = O.mixtral_forward(state, cfg.llm, state["model.embed_tokens.weight"].float()[torch.tensor([[nxt]])], past=past,
                                         last_only=True, trace=tr)
         step_ok.append(bool(_routing_stable(tr)[0]))
     rows = torch.stack(rows)

@@ -1,5 +1,6 @@
 // Library plumbing: error reporting, launch accounting, device query, TMA descriptor encoding.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -34,6 +35,15 @@ int num_sms() {
         cached = n;
     }
     return cached;
+}
+
+bool use_pdl() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("VITA_B200_PDL");
+        cached = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return cached == 1;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

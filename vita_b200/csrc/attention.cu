@@ -278,6 +278,8 @@ decode_attn_kernel(const DecodeAttnParams p) {
     __shared__ int s_last;
 
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+    pdl_launch_dependents();
+    pdl_wait();   // q and the newest K/V row come from the QKV kernel
     const int ctx = p.cur_pos[b] + 1;
     const int per = (ctx + p.splits - 1) / p.splits;
     const int k_begin = split * per;
@@ -480,6 +482,7 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
     p.splits = (int)splits;
     p.scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((unsigned)splits, (unsigned)n_kv_heads, (unsigned)B);
-    decode_attn_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    cudaError_t e = launch_chain(decode_attn_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p);
+    if (e != cudaSuccess) return check_cuda(e, "decode_attn_kernel");
     return check_launch("decode_attn_kernel");
 }

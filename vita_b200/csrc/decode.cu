@@ -126,9 +126,11 @@ stream_gemv_kernel(const Op op) {
         fence_barrier_init();
     }
     __syncthreads();
+    pdl_launch_dependents();   // the next kernel of the decode chain may start filling its weight ring
 
     if (warp == GV_CONSUMERS / 32) {
         if (lane == 0) {
+            if (Op::kProducerReadsUpstream) pdl_wait();   // row addresses depend on the previous kernel's output
             if (Op::kProducerNeedsPrologue) mbar_wait(aux_bar, 0, 13);
             int stage = 0;
             uint32_t phase = 0;
@@ -150,6 +152,7 @@ stream_gemv_kernel(const Op op) {
     }
 
     // ---------------------------------------------------------------- consumers (512 threads, 2 groups of 8 warps)
+    pdl_wait();   // activations come from the previous kernel; weights (producer warp) do not
     op.prologue(b, sm, i0, i1);
     consumer_barrier_all();
     FinishState st{-INFINITY, 0x7fffffff};
@@ -232,6 +235,7 @@ stream_gemv_kernel(const Op op) {
 
 // ------------------------------------------------------------------------------------------------ ops
 struct QkvOp {
+    static constexpr bool kProducerReadsUpstream = false;
     static constexpr bool kXPerRow = false;
     static constexpr bool kProducerNeedsPrologue = false;
     const __nv_bfloat16* h;       // [B, H]
@@ -290,6 +294,7 @@ struct QkvOp {
 };
 
 struct OProjOp {
+    static constexpr bool kProducerReadsUpstream = false;
     static constexpr bool kXPerRow = false;
     static constexpr bool kProducerNeedsPrologue = false;
     const __nv_bfloat16* x;  // [B, K] attention output
@@ -327,6 +332,7 @@ struct OProjOp {
 // post_attention_layernorm + router (top-2 of 8, fp32 softmax, renormalised) fused into the expert gate/up GEMV:
 // every CTA recomputes the 8 router logits (64 KB of L2-resident gate weights) instead of paying a kernel boundary.
 struct GateUpOp {
+    static constexpr bool kProducerReadsUpstream = false;
     static constexpr bool kXPerRow = false;
     static constexpr bool kProducerNeedsPrologue = true;
     const __nv_bfloat16* h;        // [B, H] residual stream (post attention)
@@ -432,6 +438,7 @@ struct GateUpOp {
 };
 
 struct DownOp {
+    static constexpr bool kProducerReadsUpstream = true;
     static constexpr bool kXPerRow = true;
     static constexpr bool kProducerNeedsPrologue = false;
     const __nv_bfloat16* act;   // [B, 2, I]
@@ -472,6 +479,7 @@ __device__ __forceinline__ unsigned long long pack_argmax(float v, int idx) {
 }
 
 struct LmHeadOp {
+    static constexpr bool kProducerReadsUpstream = false;
     static constexpr bool kXPerRow = false;
     static constexpr bool kProducerNeedsPrologue = false;
     const __nv_bfloat16* h;        // rows of the residual stream, row b at h + b * h_stride
@@ -522,7 +530,8 @@ static int launch_stream_gemv(const Op& op, int x_elems, int B, cudaStream_t st,
         configured_bytes = smem_bytes;
     }
     dim3 grid(num_sms(), B);
-    kern<<<grid, GV_THREADS, smem_bytes, st>>>(op);
+    cudaError_t e = launch_chain(kern, grid, dim3(GV_THREADS), smem_bytes, st, op);
+    if (e != cudaSuccess) return check_cuda(e, name);
     return check_launch(name);
 }
 
@@ -533,6 +542,8 @@ decode_embed_kernel(unsigned long long* best, int* token_log, int* gen_count, in
                     int* cur_pos, const __nv_bfloat16* embed, __nv_bfloat16* h, int H, int vocab) {
     const int b = blockIdx.x;
     __shared__ int s_tok;
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x == 0) {
         const unsigned long long key = best[b];
         int tok = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull));
@@ -615,9 +626,11 @@ extern "C" int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* ge
                                  int64_t H, int64_t vocab, void* stream) {
     VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
     if (B == 0) return VITA_OK;
-    decode_embed_kernel<<<static_cast<unsigned>(B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<unsigned long long*>(best), token_log, gen_count, (int)max_log, cache_len, cur_pos,
-        BF16C(embed), static_cast<__nv_bfloat16*>(h), (int)H, (int)vocab);
+    cudaError_t e = launch_chain(decode_embed_kernel, dim3(static_cast<unsigned>(B)), dim3(256), 0,
+                                 static_cast<cudaStream_t>(stream), reinterpret_cast<unsigned long long*>(best),
+                                 token_log, gen_count, (int)max_log, cache_len, cur_pos, BF16C(embed),
+                                 static_cast<__nv_bfloat16*>(h), (int)H, (int)vocab);
+    if (e != cudaSuccess) return check_cuda(e, "decode_embed");
     return check_launch("decode_embed");
 }
 

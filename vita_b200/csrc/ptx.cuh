@@ -142,6 +142,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// No-ops unless the kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
