@@ -158,6 +158,29 @@ int vita_decode_moe_down(const void* act, const void* w2, const int32_t* topk_id
 int vita_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
                         uint64_t* best, int64_t B, int64_t H, int64_t V, float eps, void* stream);
 
+/* ---- greedy decode step on the tensor cores (tcgen05 swap-AB GEMV, stream-K) ---------------------------------
+ * Same operations and epilogues as the vita_decode_* entry points above, with the weight tile as the M operand of
+ * tcgen05.mma and the activation vector as row 0 of a 16-wide N operand; (row-block, k-block) units are split evenly
+ * over all SMs and combined through `workspace` (vita_decode_tc_workspace_bytes, zero-initialised once, shared by all
+ * five calls; ws_row_blocks = the max_row_blocks it was sized for).  K multiples of 64. */
+int64_t vita_decode_tc_workspace_bytes(int64_t B, int64_t max_row_blocks);
+int vita_decode_tc_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, const float* cos_sin,
+                            const int32_t* cur_pos, const int32_t* block_table, void* q_out, void* k_cache,
+                            void* v_cache, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H,
+                            int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim, int64_t page_size,
+                            int64_t max_pages, float eps, void* stream);
+int vita_decode_tc_oproj(const void* x, const void* w, void* h, void* workspace, int64_t ws_row_blocks, int64_t B,
+                         int64_t N, int64_t K, void* stream);
+int vita_decode_tc_moe_gate_up(const void* h, const void* norm_w, const void* gate_w, const void* w13,
+                               int32_t* topk_ids, float* topk_w, void* act, void* workspace, int64_t ws_row_blocks,
+                               int64_t B, int64_t H, int64_t I, int64_t E, float eps, void* stream);
+int vita_decode_tc_moe_down(const void* act, const void* w2, const int32_t* topk_ids, const float* topk_w, void* h,
+                            void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H, int64_t I, int64_t E,
+                            void* stream);
+int vita_tc_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
+                           uint64_t* best, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H, int64_t V,
+                           float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,10 +229,12 @@ def test_full_width_mixtral_two_layers_prefill_and_decode_match_oracle():
         out = model(input_ids=torch.tensor([[t]]), past_key_values=out.past_key_values)
         got.append(out.logits[0, -1].float().cpu())
     got = torch.stack(got)
-    # row i of `got`/`rows` are the logits token i was chosen from; they depend on the routing of steps < i
-    usable = torch.tensor([bool(stable[-1])] + [all(step_ok[:i]) and bool(stable[-1]) for i in range(1, n_new)])
+    # row 0 comes out of the forward of the last prompt token, row i >= 1 out of decode step i-1: compare the rows
+    # whose own forward had clear routing (flips of *other* tokens only reach them through attention, second order)
+    usable = torch.tensor([bool(stable[-1])] + [step_ok[i - 1] for i in range(1, n_new)])
     err = (got - rows).abs().amax(-1) / rows.abs().max()
     print(f"decode: usable steps {usable.tolist()}, rel err {err.tolist()}")
+    assert usable.float().mean() >= 0.5
     if usable.any():
         assert err[usable].max() < 6e-2
         clear = _margin_ok(rows, 0.05 * rows.abs().max()) & usable

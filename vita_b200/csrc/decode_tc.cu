@@ -1,0 +1,665 @@
+// Decode-step linears on the 5th-gen tensor cores ("swap-AB" GEMV, stream-K):  y[rows] = W[rows, K] . x[K].
+//
+// The SIMT version of these kernels (decode.cu) moved every byte at full TMA rate but needed ~80 issue slots per
+// 32 bytes of weights for bf16->fp32 unpacking and FMAs, which capped it at ~65% of HBM bandwidth (ncu: 48% issue
+// utilisation at 60% DRAM throughput).  Here the weight tile is the *M* operand of tcgen05.mma (128 rows x 64 k,
+// TMA-loaded with the 128B swizzle) and the activation vector is row 0 of a 16 x 64 *N* operand tile, so the CUDA
+// cores only run the per-row epilogue:
+//   warp 0  TMA producer: streams W tiles into an smem ring (starts before the PDL dependency resolves: weights
+//           never depend on the previous kernel, except for the expert ids which it waits for);
+//   warp 1  MMA issuer: per ring stage, 4 x tcgen05.mma.kind::f16 (M=128, N=16, K=16) per part into TMEM;
+//   warp 2  TMEM allocator;
+//   warp 3  x-tile writer: copies 128 B of the (bf16, smem-resident) activation vector into row 0 of the stage's
+//           N tile (rows 1..15 stay zero), fence.proxy.async, arrives on the stage barrier;
+//   warps 4-7  prologue (RMSNorm / router / residual prefetch) and epilogue: tcgen05.ld, fused per-row epilogue.
+// Work is cut stream-K style: the (row-block, k-block) units are split evenly and contiguously over the CTAs, so all
+// 148 SMs stream the same number of bytes whatever the matrix shape.  A row block whose K range spans several CTAs
+// is combined through per-contributor scratch slots and a ticket; the last contributor sums the slots in a fixed
+// order (deterministic) and runs the epilogue.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vita {
+
+constexpr int TC_XN = 16;                 // N of the MMA (activation tile rows; row 0 carries x)
+constexpr int TC_A_BYTES = 128 * 64 * 2;  // one weight tile
+constexpr int TC_X_BYTES = TC_XN * 64 * 2;
+constexpr int TC_SLOTS = 8;               // max contributors per row block
+constexpr int TC_THREADS = 256;
+
+__device__ __forceinline__ void tmem_ld_32x32_x1(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// sum over the 128 epilogue threads (warps 4..7); scratch >= 4 floats
+__device__ __forceinline__ float epi_sum(float v, float* scratch) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) scratch[(threadIdx.x >> 5) - 4] = v;
+    epi_barrier();
+    const float t = scratch[0] + scratch[1] + scratch[2] + scratch[3];
+    epi_barrier();
+    return t;
+}
+
+struct TcSmem {
+    __nv_bfloat16* xs;  // compact activation vector(s)
+    float* scratch;     // 64 floats
+    float* prep;        // 256 floats
+    int* misc;          // 8 ints
+    float* pair;        // 128 floats (row exchange inside a row block)
+};
+
+__device__ __forceinline__ void tc_load_x_rmsnorm(const __nv_bfloat16* h, const __nv_bfloat16* w, __nv_bfloat16* xs,
+                                                  int K, float eps, float* scratch) {
+    const int t = threadIdx.x - 128;
+    float ss = 0.0f;
+    for (int i = t * 8; i < K; i += 128 * 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(h + i);
+        const uint32_t a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ss += bf16_lo(a[e]) * bf16_lo(a[e]) + bf16_hi(a[e]) * bf16_hi(a[e]);
+    }
+    const float inv = rsqrtf(epi_sum(ss, scratch) / static_cast<float>(K) + eps);
+    for (int i = t * 8; i < K; i += 128 * 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(h + i);
+        const uint4 g = __ldg(reinterpret_cast<const uint4*>(w + i));
+        const uint32_t a[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w};
+        uint4 o;
+        uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            op[e] = pack_bf16(bf16_lo(a[e]) * inv * bf16_lo(gg[e]), bf16_hi(a[e]) * inv * bf16_hi(gg[e]));
+        *reinterpret_cast<uint4*>(xs + i) = o;
+    }
+}
+__device__ __forceinline__ void tc_load_x_copy(const __nv_bfloat16* src, __nv_bfloat16* xs, int n) {
+    for (int i = (threadIdx.x - 128) * 8; i < n; i += 128 * 8)
+        *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(src + i);
+}
+
+struct TcFinish {
+    float best;
+    int best_idx;
+};
+
+// PARTS: weight tiles per unit (1, or 2 for gate|up and for the two experts of the down projection).
+// XPARTS: distinct activation vectors (2 only for the down projection).
+template <class Op>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __restrict__ g_scratch,
+               int* __restrict__ g_tickets) {
+    constexpr int PARTS = Op::kParts, XPARTS = Op::kXParts, STAGES = Op::kStages;
+    constexpr int STAGE_A = PARTS * TC_A_BYTES;
+    constexpr int STAGE_X = XPARTS * TC_X_BYTES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sX = sA + STAGES * STAGE_A;
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(sX + STAGES * STAGE_X);
+    uint8_t* tail = reinterpret_cast<uint8_t*>(xs) + ((op.x_elems() * 2 + 127) / 128) * 128;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* x_ready = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
+    float* scratch = reinterpret_cast<float*>(tmem_slot + 2);
+    float* prep = scratch + 64;
+    float* pair = prep + 256;
+    int* misc = reinterpret_cast<int*>(pair + 128);
+    TcSmem sm{xs, scratch, prep, misc, pair};
+
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = op.K;
+    const int n_kb = K >> 6;
+    const int n_rb = op.num_row_blocks();
+    const long long U = static_cast<long long>(n_rb) * n_kb;
+    const int G = gridDim.x;
+    const long long u0 = U * blockIdx.x / G, u1 = U * (blockIdx.x + 1) / G;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 2);   // TMA producer (expect_tx) + x-tile writer
+            mbar_init(&empty_bar[i], 1);  // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_init(x_ready, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 64);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer (weights)
+            if (Op::kRowsNeedPrologue) mbar_wait(x_ready, 0, 21);      // expert ids computed by this CTA's prologue
+            else if (Op::kRowsNeedUpstream) pdl_wait();                 // expert ids written by the previous kernel
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long u = u0; u < u1; ++u) {
+                const int rb = static_cast<int>(u / n_kb), kb = static_cast<int>(u % n_kb);
+                mbar_wait(&empty_bar[stage], phase ^ 1, 22);
+                mbar_arrive_expect_tx(&full_bar[stage], STAGE_A);
+#pragma unroll
+                for (int p = 0; p < PARTS; ++p)
+                    tma_load_2d(sA + stage * STAGE_A + p * TC_A_BYTES, &tmW, &full_bar[stage], kb * 64,
+                                op.a_row(b, rb, p, sm));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = umma_idesc_bf16(128, TC_XN);
+            const uint32_t sA_addr = smem_u32(sA), sX_addr = smem_u32(sX);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            long long u = u0;
+            while (u < u1) {
+                const int rb = static_cast<int>(u / n_kb);
+                long long seg_end = static_cast<long long>(rb + 1) * n_kb;
+                if (seg_end > u1) seg_end = u1;
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1, 23);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 32;
+                for (long long v = u; v < seg_end; ++v) {
+                    mbar_wait(&full_bar[stage], phase, 24);
+                    tc_fence_after();
+#pragma unroll
+                    for (int p = 0; p < PARTS; ++p) {
+                        const uint64_t da = umma_desc_k_sw128(sA_addr + stage * STAGE_A + p * TC_A_BYTES);
+                        const uint64_t dx = umma_desc_k_sw128(sX_addr + stage * STAGE_X + (XPARTS > 1 ? p : 0) * TC_X_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16(d_tmem + p * TC_XN, da + 2 * k, dx + 2 * k, idesc, (v > u || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&acc_full[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                u = seg_end;
+            }
+        }
+    } else if (warp == 3) {
+        // ---------------------------------------------------------------- x-tile writer
+        // zero the N tiles once (rows 1..15 stay zero for the whole kernel), then per stage copy 128 B into row 0
+        for (int i = lane; i < STAGES * STAGE_X / 16; i += 32) reinterpret_cast<uint4*>(sX)[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        __syncwarp();
+        mbar_wait(x_ready, 0, 25);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long u = u0; u < u1; ++u) {
+            const int kb = static_cast<int>(u % n_kb);
+            mbar_wait(&empty_bar[stage], phase ^ 1, 26);
+            if (lane < 8 * XPARTS) {
+                const int px = lane >> 3, c = lane & 7;
+                *reinterpret_cast<uint4*>(sX + stage * STAGE_X + px * TC_X_BYTES + c * 16) =
+                    *reinterpret_cast<const uint4*>(xs + static_cast<long long>(px) * K + kb * 64 + c * 8);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- prologue + epilogue (128 threads)
+        pdl_wait();   // activations come from the previous kernel
+        op.prologue(b, sm);
+        __threadfence_block();
+        epi_barrier();
+        if (threadIdx.x == 128) mbar_arrive(x_ready);
+
+        const int quad = warp - 4;
+        const int row = quad * 32 + lane;
+        TcFinish st{-INFINITY, 0x7fffffff};
+        float* my_scratch = g_scratch + static_cast<long long>(b) * n_rb * TC_SLOTS * PARTS * 128;
+        int* my_tickets = g_tickets + static_cast<long long>(b) * n_rb;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        long long u = u0;
+        while (u < u1) {
+            const int rb = static_cast<int>(u / n_kb);
+            const long long rb_begin = static_cast<long long>(rb) * n_kb, rb_end = rb_begin + n_kb;
+            const long long seg_end = rb_end < u1 ? rb_end : u1;
+            mbar_wait(&acc_full[acc], acc_phase, 27);
+            tc_fence_after();
+            float v[PARTS];
+#pragma unroll
+            for (int p = 0; p < PARTS; ++p) {
+                uint32_t r;
+                tmem_ld_32x32_x1(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 32 + p * TC_XN, r);
+                v[p] = __uint_as_float(r);
+            }
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+
+            bool do_finish = true;
+            if (u != rb_begin || seg_end != rb_end) {
+                // partial K range: publish to this CTA's slot; the last contributor reduces all slots in order
+                int c_first = blockIdx.x;
+                while (c_first > 0 && U * c_first / G > rb_begin) --c_first;
+                int c_last = blockIdx.x;
+                while (c_last + 1 < G && U * (c_last + 1) / G < rb_end) ++c_last;
+                const int slot = blockIdx.x - c_first, n_contrib = c_last - c_first + 1;
+                float* base = my_scratch + static_cast<long long>(rb) * TC_SLOTS * PARTS * 128;
+#pragma unroll
+                for (int p = 0; p < PARTS; ++p) __stcg(base + (slot * PARTS + p) * 128 + row, v[p]);
+                __threadfence();
+                epi_barrier();
+                if (threadIdx.x == 128) {
+                    const int t = atomicAdd(&my_tickets[rb], 1);
+                    misc[7] = (t == n_contrib - 1);
+                    if (t == n_contrib - 1) my_tickets[rb] = 0;
+                }
+                epi_barrier();
+                do_finish = misc[7] != 0;
+                if (do_finish) {
+                    __threadfence();
+#pragma unroll
+                    for (int p = 0; p < PARTS; ++p) {
+                        float s = 0.0f;
+                        for (int q = 0; q < n_contrib; ++q) s += __ldcg(base + (q * PARTS + p) * 128 + row);
+                        v[p] = s;
+                    }
+                }
+                epi_barrier();   // misc[7] may be rewritten by the next segment
+            }
+            if (do_finish) op.finish(b, rb, row, v, st, sm);
+            u = seg_end;
+        }
+        op.finalize(b, st);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 64);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ ops
+struct TcQkvOp {
+    static constexpr int kParts = 1, kXParts = 1, kStages = 10;
+    static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
+    const __nv_bfloat16* h;
+    const __nv_bfloat16* norm_w;
+    const float* cos_sin;
+    const int* cur_pos;
+    const int* block_table;
+    __nv_bfloat16* q_out;
+    __nv_bfloat16* k_cache;
+    __nv_bfloat16* v_cache;
+    int K, n_q, n_kv, page_size, max_pages;
+    float eps;
+
+    __device__ int x_elems() const { return K; }
+    __device__ int num_row_blocks() const { return n_q + 2 * n_kv; }   // one 128-row block per head
+    __device__ int a_row(int, int rb, int, const TcSmem&) const { return rb * 128; }
+    __device__ void prologue(int b, const TcSmem& sm) const {
+        const int t = threadIdx.x - 128;
+        const int pos = cur_pos[b];
+        sm.prep[t] = cos_sin[static_cast<long long>(pos) * 128 + t];
+        if (t == 0) {
+            const int page = block_table[static_cast<long long>(b) * max_pages + pos / page_size];
+            sm.misc[0] = page * page_size + pos % page_size;
+        }
+        tc_load_x_rmsnorm(h + static_cast<long long>(b) * K, norm_w, sm.xs, K, eps, sm.scratch);
+    }
+    __device__ void finish(int b, int rb, int row, const float (&v)[1], TcFinish&, const TcSmem& sm) const {
+        // projections are rounded to bf16 before RoPE, as the GEMM path (and the reference) does
+        const float x = __bfloat162float(__float2bfloat16(v[0]));
+        float o = x;
+        if (rb < n_q + n_kv) {   // rotate-half RoPE: partner row is row ^ 64 of the same head
+            sm.pair[row] = x;
+            epi_barrier();
+            const float partner = sm.pair[row ^ 64];
+            const int j = row & 63;
+            const float c = sm.prep[j], s = sm.prep[64 + j];
+            o = (row < 64) ? x * c - partner * s : x * c + partner * s;
+            epi_barrier();
+        }
+        if (rb < n_q) {
+            q_out[(static_cast<long long>(b) * n_q + rb) * 128 + row] = __float2bfloat16(o);
+        } else {
+            const long long slot = sm.misc[0];
+            const bool is_k = rb < n_q + n_kv;
+            const int kvh = is_k ? rb - n_q : rb - n_q - n_kv;
+            ((is_k ? k_cache : v_cache) + (slot * n_kv + kvh) * 128)[row] = __float2bfloat16(o);
+        }
+    }
+    __device__ void finalize(int, TcFinish&) const {}
+};
+
+struct TcOProjOp {
+    static constexpr int kParts = 1, kXParts = 1, kStages = 10;
+    static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
+    const __nv_bfloat16* x;
+    __nv_bfloat16* h;
+    int K, N;
+
+    __device__ int x_elems() const { return K; }
+    __device__ int num_row_blocks() const { return (N + 127) / 128; }
+    __device__ int a_row(int, int rb, int, const TcSmem&) const { return rb * 128; }
+    __device__ void prologue(int b, const TcSmem& sm) const { tc_load_x_copy(x + static_cast<long long>(b) * K, sm.xs, K); }
+    __device__ void finish(int b, int rb, int row, const float (&v)[1], TcFinish&, const TcSmem&) const {
+        const int r = rb * 128 + row;
+        if (r < N) {
+            __nv_bfloat16* hr = h + static_cast<long long>(b) * N + r;
+            *hr = __float2bfloat16(__bfloat162float(*hr) + v[0]);
+        }
+    }
+    __device__ void finalize(int, TcFinish&) const {}
+};
+
+struct TcGateUpOp {
+    static constexpr int kParts = 2, kXParts = 1, kStages = 5;
+    static constexpr bool kRowsNeedPrologue = true, kRowsNeedUpstream = false;
+    const __nv_bfloat16* h;
+    const __nv_bfloat16* norm_w;
+    const __nv_bfloat16* gate_w;   // [8, H]
+    int* topk_ids;
+    float* topk_w;
+    __nv_bfloat16* act;            // [B, 2, I]
+    int K, I;
+    float eps;
+
+    __device__ int x_elems() const { return K; }
+    __device__ int num_row_blocks() const { return 2 * (I / 128); }
+    __device__ int a_row(int, int rb, int p, const TcSmem& sm) const {
+        const int nb = I / 128, k = rb / nb, jb = rb % nb;
+        return sm.misc[k] * 2 * I + p * I + jb * 128;   // rows of the fused [E * 2I, H] weight
+    }
+    __device__ void prologue(int b, const TcSmem& sm) const {
+        const int t = threadIdx.x - 128;
+        const __nv_bfloat16* hr = h + static_cast<long long>(b) * K;
+        float part[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) part[e] = 0.0f;
+        for (int i = t * 8; i < K; i += 128 * 8) {
+            const uint4 hv = *reinterpret_cast<const uint4*>(hr + i);
+            const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w + i));
+            const uint32_t a[4] = {hv.x, hv.y, hv.z, hv.w}, gg[4] = {g.x, g.y, g.z, g.w};
+            float xw[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float lo = bf16_lo(a[q]), hi = bf16_hi(a[q]);
+                part[0] += lo * lo + hi * hi;
+                xw[2 * q] = lo * bf16_lo(gg[q]);
+                xw[2 * q + 1] = hi * bf16_hi(gg[q]);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint4 ge = __ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * K + i));
+                const uint32_t w[4] = {ge.x, ge.y, ge.z, ge.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) part[1 + e] += xw[2 * q] * bf16_lo(w[q]) + xw[2 * q + 1] * bf16_hi(w[q]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 9; ++e) part[e] = warp_sum(part[e]);
+        const int w4 = (threadIdx.x >> 5) - 4;
+        if ((threadIdx.x & 31) == 0)
+#pragma unroll
+            for (int e = 0; e < 9; ++e) sm.prep[w4 * 9 + e] = part[e];
+        epi_barrier();
+        float tot[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) tot[e] = sm.prep[e] + sm.prep[9 + e] + sm.prep[18 + e] + sm.prep[27 + e];
+        const float inv = rsqrtf(tot[0] / static_cast<float>(K) + eps);
+        float p[8], m = -INFINITY, sum = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { p[e] = tot[1 + e] * inv; m = fmaxf(m, p[e]); }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { p[e] = expf(p[e] - m); sum += p[e]; }
+        int e0 = 0;
+#pragma unroll
+        for (int e = 1; e < 8; ++e) if (p[e] > p[e0]) e0 = e;
+        int e1 = (e0 == 0) ? 1 : 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (e != e0 && p[e] > p[e1]) e1 = e;
+        if (t == 0) {
+            sm.misc[0] = e0;
+            sm.misc[1] = e1;
+            if (blockIdx.x == 0) {
+                const float p0 = p[e0] / sum, p1 = p[e1] / sum, den = p0 + p1;
+                topk_ids[b * 2] = e0;
+                topk_ids[b * 2 + 1] = e1;
+                topk_w[b * 2] = p0 / den;
+                topk_w[b * 2 + 1] = p1 / den;
+            }
+        }
+        for (int i = t * 8; i < K; i += 128 * 8) {
+            const uint4 hv = *reinterpret_cast<const uint4*>(hr + i);
+            const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w + i));
+            const uint32_t a[4] = {hv.x, hv.y, hv.z, hv.w}, gg[4] = {g.x, g.y, g.z, g.w};
+            uint4 o;
+            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                op[q] = pack_bf16(bf16_lo(a[q]) * inv * bf16_lo(gg[q]), bf16_hi(a[q]) * inv * bf16_hi(gg[q]));
+            *reinterpret_cast<uint4*>(sm.xs + i) = o;
+        }
+    }
+    __device__ void finish(int b, int rb, int row, const float (&v)[2], TcFinish&, const TcSmem&) const {
+        const int nb = I / 128, k = rb / nb, jb = rb % nb;
+        act[(static_cast<long long>(b) * 2 + k) * I + jb * 128 + row] = __float2bfloat16(silu(v[0]) * v[1]);
+    }
+    __device__ void finalize(int, TcFinish&) const {}
+};
+
+struct TcDownOp {
+    static constexpr int kParts = 2, kXParts = 2, kStages = 4;
+    static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = true;
+    const __nv_bfloat16* act;   // [B, 2, I]
+    const int* topk_ids;
+    const float* topk_w;
+    __nv_bfloat16* h;
+    int K, H;                   // K = I
+
+    __device__ int x_elems() const { return 2 * K; }
+    __device__ int num_row_blocks() const { return (H + 127) / 128; }
+    __device__ int a_row(int b, int rb, int p, const TcSmem&) const { return topk_ids[b * 2 + p] * H + rb * 128; }
+    __device__ void prologue(int b, const TcSmem& sm) const {
+        const int t = threadIdx.x - 128;
+        if (t < 2) sm.prep[t] = topk_w[b * 2 + t];
+        tc_load_x_copy(act + static_cast<long long>(b) * 2 * K, sm.xs, 2 * K);
+    }
+    __device__ void finish(int b, int rb, int row, const float (&v)[2], TcFinish&, const TcSmem& sm) const {
+        const int r = rb * 128 + row;
+        if (r < H) {
+            __nv_bfloat16* hr = h + static_cast<long long>(b) * H + r;
+            *hr = __float2bfloat16(__bfloat162float(*hr) + sm.prep[0] * v[0] + sm.prep[1] * v[1]);
+        }
+    }
+    __device__ void finalize(int, TcFinish&) const {}
+};
+
+__device__ __forceinline__ unsigned long long tc_pack_argmax(float v, int idx) {
+    uint32_t u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return (static_cast<unsigned long long>(u) << 32) |
+           static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(idx));
+}
+
+struct TcLmHeadOp {
+    static constexpr int kParts = 1, kXParts = 1, kStages = 10;
+    static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
+    const __nv_bfloat16* h;
+    long long h_stride;
+    const __nv_bfloat16* norm_w;
+    __nv_bfloat16* logits;
+    unsigned long long* best;
+    int K, V;
+    float eps;
+
+    __device__ int x_elems() const { return K; }
+    __device__ int num_row_blocks() const { return (V + 127) / 128; }
+    __device__ int a_row(int, int rb, int, const TcSmem&) const { return rb * 128; }
+    __device__ void prologue(int b, const TcSmem& sm) const {
+        tc_load_x_rmsnorm(h + static_cast<long long>(b) * h_stride, norm_w, sm.xs, K, eps, sm.scratch);
+    }
+    __device__ void finish(int b, int rb, int row, const float (&v)[1], TcFinish& st, const TcSmem&) const {
+        const int r = rb * 128 + row;
+        if (r >= V) return;
+        const __nv_bfloat16 l = __float2bfloat16(v[0]);   // logits stay bf16; arg-max runs on them
+        if (logits) logits[static_cast<long long>(b) * V + r] = l;
+        const float f = __bfloat162float(l);
+        if (f > st.best || (f == st.best && r < st.best_idx)) { st.best = f; st.best_idx = r; }
+    }
+    __device__ void finalize(int b, TcFinish& st) const {
+        // warp arg-max, then one atomic per warp
+        float bv = st.best;
+        int bi = st.best_idx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0 && bi != 0x7fffffff) atomicMax(&best[b], tc_pack_argmax(bv, bi));
+    }
+};
+
+struct TcWorkspace {
+    float* scratch;
+    int* tickets;
+};
+
+template <class Op>
+static int launch_tc(const Op& op, const void* W, long long w_rows, int K, int n_rb, int x_elems, int B,
+                     const TcWorkspace& ws, cudaStream_t st, const char* name) {
+    CUtensorMap tm;
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(w_rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = make_tensor_map_bf16(&tm, W, 2, dims, strides, box, true);
+    if (rc) return rc;
+    const int smem_bytes = Op::kStages * (Op::kParts * TC_A_BYTES + Op::kXParts * TC_X_BYTES) +
+                           ((x_elems * 2 + 127) / 128) * 128 + (2 * Op::kStages + 5) * 8 + 8 +
+                           (64 + 256 + 128 + 8) * 4 + 1024 + 128;
+    auto kern = tc_gemv_kernel<Op>;
+    static int configured = 0;
+    if (smem_bytes > configured) {
+        rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), name);
+        if (rc) return rc;
+        configured = smem_bytes;
+    }
+    // keep the number of contributors per row block <= TC_SLOTS: every CTA gets at least ceil(n_kb / 6) units
+    const int n_kb = K / 64;
+    const long long U = static_cast<long long>(n_rb) * n_kb;
+    const int min_units = (n_kb + 5) / 6;
+    long long g = U / (min_units > 0 ? min_units : 1);
+    if (g > num_sms()) g = num_sms();
+    if (g < 1) g = 1;
+    dim3 grid(static_cast<unsigned>(g), B);
+    cudaError_t e = launch_chain(kern, grid, dim3(TC_THREADS), smem_bytes, st, tm, op, ws.scratch, ws.tickets);
+    if (e != cudaSuccess) return check_cuda(e, name);
+    return check_launch(name);
+}
+
+static inline bool tc_shape_ok(long long K) { return K % 64 == 0 && K >= 64; }
+
+}  // namespace vita
+
+using namespace vita;
+
+// workspace: [tickets: B * max_rb ints][scratch: B * max_rb * SLOTS * 2 * 128 floats]; zero-initialised once.
+extern "C" int64_t vita_decode_tc_workspace_bytes(int64_t B, int64_t max_row_blocks) {
+    return ((B * max_row_blocks * 4 + 255) / 256) * 256 + B * max_row_blocks * TC_SLOTS * 2 * 128 * 4;
+}
+
+static TcWorkspace split_ws(void* workspace, int64_t B, int64_t max_rb) {
+    TcWorkspace ws;
+    ws.tickets = static_cast<int*>(workspace);
+    ws.scratch = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((B * max_rb * 4 + 255) / 256) * 256);
+    return ws;
+}
+
+extern "C" int vita_decode_tc_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, const float* cos_sin,
+                                       const int32_t* cur_pos, const int32_t* block_table, void* q_out, void* k_cache,
+                                       void* v_cache, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H,
+                                       int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim, int64_t page_size,
+                                       int64_t max_pages, float eps, void* stream) {
+    VITA_REQUIRE(head_dim == 128 && tc_shape_ok(H), "head_dim must be 128 and H a multiple of 64");
+    const int n_rb = static_cast<int>(n_q_heads + 2 * n_kv_heads);
+    VITA_REQUIRE(workspace && n_rb <= ws_row_blocks, "workspace too small");
+    if (B == 0) return VITA_OK;
+    TcQkvOp op{BF16C(h), BF16C(norm_w), cos_sin, cur_pos, block_table, static_cast<__nv_bfloat16*>(q_out),
+               static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), (int)H, (int)n_q_heads,
+               (int)n_kv_heads, (int)page_size, (int)max_pages, eps};
+    return launch_tc(op, w_qkv, n_rb * 128ll, (int)H, n_rb, (int)H, (int)B, split_ws(workspace, B, ws_row_blocks),
+                     static_cast<cudaStream_t>(stream), "decode_tc_qkv_rope");
+}
+
+extern "C" int vita_decode_tc_oproj(const void* x, const void* w, void* h, void* workspace, int64_t ws_row_blocks,
+                                    int64_t B, int64_t N, int64_t K, void* stream) {
+    VITA_REQUIRE(tc_shape_ok(K), "K must be a multiple of 64");
+    const int n_rb = static_cast<int>((N + 127) / 128);
+    VITA_REQUIRE(workspace && n_rb <= ws_row_blocks, "workspace too small");
+    if (B == 0) return VITA_OK;
+    TcOProjOp op{BF16C(x), static_cast<__nv_bfloat16*>(h), (int)K, (int)N};
+    return launch_tc(op, w, N, (int)K, n_rb, (int)K, (int)B, split_ws(workspace, B, ws_row_blocks),
+                     static_cast<cudaStream_t>(stream), "decode_tc_oproj");
+}
+
+extern "C" int vita_decode_tc_moe_gate_up(const void* h, const void* norm_w, const void* gate_w, const void* w13,
+                                          int32_t* topk_ids, float* topk_w, void* act, void* workspace,
+                                          int64_t ws_row_blocks, int64_t B, int64_t H, int64_t I, int64_t E, float eps,
+                                          void* stream) {
+    VITA_REQUIRE(E == 8, "router is specialised for 8 experts (Mixtral-8x7B)");
+    VITA_REQUIRE(tc_shape_ok(H) && I % 128 == 0, "H must be a multiple of 64 and I a multiple of 128");
+    const int n_rb = static_cast<int>(2 * (I / 128));
+    VITA_REQUIRE(workspace && n_rb <= ws_row_blocks, "workspace too small");
+    if (B == 0) return VITA_OK;
+    TcGateUpOp op{BF16C(h), BF16C(norm_w), BF16C(gate_w), topk_ids, topk_w, static_cast<__nv_bfloat16*>(act), (int)H,
+                  (int)I, eps};
+    return launch_tc(op, w13, E * 2 * I, (int)H, n_rb, (int)H, (int)B, split_ws(workspace, B, ws_row_blocks),
+                     static_cast<cudaStream_t>(stream), "decode_tc_moe_gate_up");
+}
+
+extern "C" int vita_decode_tc_moe_down(const void* act, const void* w2, const int32_t* topk_ids, const float* topk_w,
+                                       void* h, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H,
+                                       int64_t I, int64_t E, void* stream) {
+    VITA_REQUIRE(tc_shape_ok(I) && H % 128 == 0, "I must be a multiple of 64 and H a multiple of 128");
+    const int n_rb = static_cast<int>(H / 128);
+    VITA_REQUIRE(workspace && n_rb <= ws_row_blocks, "workspace too small");
+    if (B == 0) return VITA_OK;
+    TcDownOp op{BF16C(act), topk_ids, topk_w, static_cast<__nv_bfloat16*>(h), (int)I, (int)H};
+    return launch_tc(op, w2, E * H, (int)I, n_rb, (int)(2 * I), (int)B, split_ws(workspace, B, ws_row_blocks),
+                     static_cast<cudaStream_t>(stream), "decode_tc_moe_down");
+}
+
+extern "C" int vita_tc_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
+                                      uint64_t* best, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H,
+                                      int64_t V, float eps, void* stream) {
+    VITA_REQUIRE(tc_shape_ok(H), "H must be a multiple of 64");
+    const int n_rb = static_cast<int>((V + 127) / 128);
+    VITA_REQUIRE(workspace && n_rb <= ws_row_blocks, "workspace too small");
+    if (B == 0) return VITA_OK;
+    TcLmHeadOp op{BF16C(h), h_stride, BF16C(norm_w), static_cast<__nv_bfloat16*>(logits),
+                  reinterpret_cast<unsigned long long*>(best), (int)H, (int)V, eps};
+    return launch_tc(op, w, V, (int)H, n_rb, (int)H, (int)B, split_ws(workspace, B, ws_row_blocks),
+                     static_cast<cudaStream_t>(stream), "tc_lm_head_argmax");
+}

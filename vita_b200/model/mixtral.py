@@ -6,6 +6,7 @@ web_demo/vllm_tools/vllm_file/mixtral.py:375-628).  Host code only sequences ker
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -73,6 +74,11 @@ class MixtralDecoder:
         self.d_act = torch.zeros(B, 2, I, dtype=BF16, device=dev)
         self.d_logits = torch.zeros(B, cfg.vocab_size, dtype=BF16, device=dev)
         self.attn_ws = ops.decode_attention_workspace(B, cfg.num_key_value_heads, decode_splits, dev)
+        # decode linears: tcgen05 swap-AB GEMV (default) or the SIMT streaming GEMV (VITA_B200_GEMV=simt)
+        self.use_tc = os.environ.get("VITA_B200_GEMV", "tc") != "simt" and H % 64 == 0 and I % 128 == 0
+        max_rb = max((cfg.vocab_size + 127) // 128, 2 * (I // 128), cfg.num_attention_heads
+                     + 2 * cfg.num_key_value_heads, (H + 127) // 128)
+        self.tc_ws = ops.TcWorkspace(B, max_rb, dev) if self.use_tc else None
         self._graph = None
         self._graph_batch = None
         self._prefill_ws = {}
@@ -143,8 +149,12 @@ class MixtralDecoder:
         # first generated token: final norm + lm_head + arg-max on the last row only
         self.best[slot:slot + 1].zero_()
         last_logits = self.d_logits[slot:slot + 1] if (want_last_logits or all_logits) else None
-        ops.lm_head_argmax(h[S - 1:], H, w["norm"], w["lm_head"], last_logits, self.best[slot:slot + 1], 1,
-                           c.rms_norm_eps)
+        if self.use_tc:
+            ops.tc_lm_head_argmax(h[S - 1:], H, w["norm"], w["lm_head"], last_logits, self.best[slot:slot + 1], 1,
+                                  self.tc_ws, c.rms_norm_eps)
+        else:
+            ops.lm_head_argmax(h[S - 1:], H, w["norm"], w["lm_head"], last_logits, self.best[slot:slot + 1], 1,
+                               c.rms_norm_eps)
         if all_logits:
             return ops.linear(xn, w["lm_head"])      # [S, V]; xn = final RMSNorm(h) written by the last combine
         return last_logits
@@ -156,18 +166,33 @@ class MixtralDecoder:
         h = self.d_h[:B]
         ops.decode_embed(self.best[:B], self.token_log[:B], self.gen_count[:B], cache.cache_len[:B], cache.cur_pos[:B],
                          w["embed"], h)
+        tc, ws = self.use_tc, self.tc_ws
         for li, lw in enumerate(w["layers"]):
-            ops.decode_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
-                                self.d_q[:B], cache.k[li], cache.v[li], nq, nkv, D, cache.page_size, c.rms_norm_eps)
+            if tc:
+                ops.decode_tc_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
+                                       self.d_q[:B], cache.k[li], cache.v[li], ws, nq, nkv, D, cache.page_size,
+                                       c.rms_norm_eps)
+            else:
+                ops.decode_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
+                                    self.d_q[:B], cache.k[li], cache.v[li], nq, nkv, D, cache.page_size, c.rms_norm_eps)
             ops.decode_attention(self.d_q[:B], cache.k[li], cache.v[li], cache.block_table[:B], cache.cur_pos[:B],
                                  self.d_attn[:B], self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits,
                                  D ** -0.5)
-            ops.decode_oproj(self.d_attn[:B], lw["wo"], h)
-            ops.decode_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B], self.d_act[:B],
-                                   c.rms_norm_eps)
-            ops.decode_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h)
-        ops.lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], self.d_logits[:B] if want_logits else None,
-                           self.best[:B], B, c.rms_norm_eps)
+            if tc:
+                ops.decode_tc_oproj(self.d_attn[:B], lw["wo"], h, ws)
+                ops.decode_tc_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B],
+                                          self.d_act[:B], ws, c.rms_norm_eps)
+                ops.decode_tc_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h, ws)
+            else:
+                ops.decode_oproj(self.d_attn[:B], lw["wo"], h)
+                ops.decode_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B],
+                                       self.d_act[:B], c.rms_norm_eps)
+                ops.decode_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h)
+        lg = self.d_logits[:B] if want_logits else None
+        if tc:
+            ops.tc_lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, ws, c.rms_norm_eps)
+        else:
+            ops.lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, c.rms_norm_eps)
 
     @property
     def launches_per_decode_step(self) -> int:

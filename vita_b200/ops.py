@@ -261,5 +261,46 @@ def lm_head_argmax(h, h_stride, norm_w, w, logits, best, B, eps):
               _stream())
 
 
+# ------------------------------------------------------------------------------------------------ decode step (tcgen05)
+class TcWorkspace:
+    """Cross-CTA reduction scratch of the tensor-core decode kernels (zero-initialised once, self-cleaning)."""
+
+    def __init__(self, B: int, max_row_blocks: int, device):
+        n = _lib.load().vita_decode_tc_workspace_bytes(B, max_row_blocks)
+        self.buf = torch.zeros(n, dtype=torch.uint8, device=device)
+        self.max_row_blocks = max_row_blocks
+
+
+def decode_tc_qkv_rope(h, norm_w, w_qkv, cos_sin, cur_pos, block_table, q_out, k_cache, v_cache, ws, n_q, n_kv,
+                       head_dim, page_size, eps):
+    B, H = h.shape
+    _lib.call("vita_decode_tc_qkv_rope", _p(h), _p(norm_w), _p(w_qkv), _p(cos_sin), _p(cur_pos), _p(block_table),
+              _p(q_out), _p(k_cache), _p(v_cache), _p(ws.buf), ws.max_row_blocks, B, H, n_q, n_kv, head_dim, page_size,
+              block_table.shape[1], float(eps), _stream())
+
+
+def decode_tc_oproj(x, w, h, ws):
+    B, N = h.shape
+    _lib.call("vita_decode_tc_oproj", _p(x), _p(w), _p(h), _p(ws.buf), ws.max_row_blocks, B, N, w.shape[1], _stream())
+
+
+def decode_tc_moe_gate_up(h, norm_w, gate_w, w13, topk_ids, topk_w, act, ws, eps):
+    B, H = h.shape
+    _lib.call("vita_decode_tc_moe_gate_up", _p(h), _p(norm_w), _p(gate_w), _p(w13), _p(topk_ids), _p(topk_w), _p(act),
+              _p(ws.buf), ws.max_row_blocks, B, H, w13.shape[1] // 2, gate_w.shape[0], float(eps), _stream())
+
+
+def decode_tc_moe_down(act, w2, topk_ids, topk_w, h, ws):
+    B, H = h.shape
+    _lib.call("vita_decode_tc_moe_down", _p(act), _p(w2), _p(topk_ids), _p(topk_w), _p(h), _p(ws.buf),
+              ws.max_row_blocks, B, H, w2.shape[2], w2.shape[0], _stream())
+
+
+def tc_lm_head_argmax(h, h_stride, norm_w, w, logits, best, B, ws, eps):
+    V, H = w.shape
+    _lib.call("vita_tc_lm_head_argmax", _p(h), h_stride, _p(norm_w), _p(w), _p(logits), _p(best), _p(ws.buf),
+              ws.max_row_blocks, B, H, V, float(eps), _stream())
+
+
 def launch_count(reset: bool = False) -> int:
     return int(_lib.load().vita_launch_count(1 if reset else 0))
