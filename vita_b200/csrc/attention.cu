@@ -393,7 +393,7 @@ decode_attn_kernel(const DecodeAttnParams p) {
     if (!s_last) return;
     __threadfence();
     const long long sbase = (static_cast<long long>(b) * p.n_kv + kvh) * p.splits * DEC_GROUP;
-    constexpr int MAXS = 32;   // splits <= 32 (checked on the host); all loads of a head are issued before use
+    constexpr int MAXS = 16;   // splits <= 16 (checked on the host); all loads of a head are issued before use
 #pragma unroll
     for (int h = 0; h < DEC_GROUP; ++h) {
         float ms[MAXS], ls[MAXS], os[MAXS];
@@ -467,7 +467,7 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
                                      int64_t B, int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim,
                                      int64_t page_size, int64_t max_pages, int64_t splits, float scale, void* stream) {
     VITA_REQUIRE(head_dim == DEC_D && n_q_heads == n_kv_heads * DEC_GROUP, "decode attention: need D=128, GQA group 4");
-    VITA_REQUIRE(splits >= 1 && splits <= 32 && workspace != nullptr, "1 <= splits <= 32 and a workspace are required");
+    VITA_REQUIRE(splits >= 1 && splits <= 16 && workspace != nullptr, "1 <= splits <= 16 and a workspace are required");
     if (B == 0) return VITA_OK;
     DecodeAttnParams p{};
     p.q = BF16C(q); p.k_cache = BF16C(k_cache); p.v_cache = BF16C(v_cache);

@@ -48,11 +48,50 @@ struct TcSmem {
     float* prep;        // 256 floats
     int* misc;          // 8 ints
     float* pair;        // 128 floats (row exchange inside a row block)
+    uint64_t* x_ready;  // arrives once the activation vector is in smem (ops that bulk-copy x arm it themselves)
 };
 
+// bf16(rmsnorm(h) * w) -> xs.  All global loads are issued up front (each of the 128 threads owns up to 4 chunks of
+// 8 elements, kept in registers between the two passes); larger K falls back to a strided loop.
 __device__ __forceinline__ void tc_load_x_rmsnorm(const __nv_bfloat16* h, const __nv_bfloat16* w, __nv_bfloat16* xs,
                                                   int K, float eps, float* scratch) {
     const int t = threadIdx.x - 128;
+    constexpr int MAXV = 4;
+    if (K <= 128 * 8 * MAXV) {
+        uint4 hv[MAXV], gv[MAXV];
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int i = (t + j * 128) * 8;
+            if (i < K) {
+                hv[j] = *reinterpret_cast<const uint4*>(h + i);
+                gv[j] = __ldg(reinterpret_cast<const uint4*>(w + i));
+            }
+        }
+        float ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            if ((t + j * 128) * 8 < K) {
+                const uint32_t a[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ss += bf16_lo(a[e]) * bf16_lo(a[e]) + bf16_hi(a[e]) * bf16_hi(a[e]);
+            }
+        }
+        const float inv = rsqrtf(epi_sum(ss, scratch) / static_cast<float>(K) + eps);
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int i = (t + j * 128) * 8;
+            if (i < K) {
+                const uint32_t a[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w}, gg[4] = {gv[j].x, gv[j].y, gv[j].z, gv[j].w};
+                uint4 o;
+                uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    op[e] = pack_bf16(bf16_lo(a[e]) * inv * bf16_lo(gg[e]), bf16_hi(a[e]) * inv * bf16_hi(gg[e]));
+                *reinterpret_cast<uint4*>(xs + i) = o;
+            }
+        }
+        return;
+    }
     float ss = 0.0f;
     for (int i = t * 8; i < K; i += 128 * 8) {
         const uint4 v = *reinterpret_cast<const uint4*>(h + i);
@@ -73,9 +112,14 @@ __device__ __forceinline__ void tc_load_x_rmsnorm(const __nv_bfloat16* h, const 
         *reinterpret_cast<uint4*>(xs + i) = o;
     }
 }
-__device__ __forceinline__ void tc_load_x_copy(const __nv_bfloat16* src, __nv_bfloat16* xs, int n) {
-    for (int i = (threadIdx.x - 128) * 8; i < n; i += 128 * 8)
-        *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(src + i);
+// Plain copy of an activation vector: one TMA 1-D bulk copy that completes straight onto the x_ready barrier.
+__device__ __forceinline__ void tc_bulk_x(const __nv_bfloat16* src, __nv_bfloat16* xs, int n, uint64_t* bar) {
+    if (threadIdx.x == 128) {
+        mbar_arrive_expect_tx(bar, static_cast<uint32_t>(n) * 2);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(xs)), "l"(src), "r"(static_cast<uint32_t>(n) * 2), "r"(smem_u32(bar))
+                     : "memory");
+    }
 }
 
 struct TcFinish {
@@ -109,7 +153,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
     float* prep = scratch + 64;
     float* pair = prep + 256;
     int* misc = reinterpret_cast<int*>(pair + 128);
-    TcSmem sm{xs, scratch, prep, misc, pair};
+    TcSmem sm{xs, scratch, prep, misc, pair, x_ready};
 
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,6 +181,9 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
         tmem_alloc(tmem_slot, 64);
         tmem_relinquish();
     }
+    // N-operand tiles: rows 1..15 stay zero for the whole kernel, row 0 is rewritten per stage
+    for (int i = threadIdx.x; i < STAGES * STAGE_X / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sX)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -198,10 +245,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
         }
     } else if (warp == 3) {
         // ---------------------------------------------------------------- x-tile writer
-        // zero the N tiles once (rows 1..15 stay zero for the whole kernel), then per stage copy 128 B into row 0
-        for (int i = lane; i < STAGES * STAGE_X / 16; i += 32) reinterpret_cast<uint4*>(sX)[i] = make_uint4(0, 0, 0, 0);
-        fence_proxy_async_smem();
-        __syncwarp();
+        // per stage: copy 128 B of the activation vector into row 0 of the N tile
         mbar_wait(x_ready, 0, 25);
         int stage = 0;
         uint32_t phase = 0;
@@ -222,9 +266,8 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
         // ---------------------------------------------------------------- prologue + epilogue (128 threads)
         pdl_wait();   // activations come from the previous kernel
         op.prologue(b, sm);
-        __threadfence_block();
         epi_barrier();
-        if (threadIdx.x == 128) mbar_arrive(x_ready);
+        if (!Op::kBulkX && threadIdx.x == 128) mbar_arrive(x_ready);
 
         const int quad = warp - 4;
         const int row = quad * 32 + lane;
@@ -265,17 +308,16 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
                 float* base = my_scratch + static_cast<long long>(rb) * TC_SLOTS * PARTS * 128;
 #pragma unroll
                 for (int p = 0; p < PARTS; ++p) __stcg(base + (slot * PARTS + p) * 128 + row, v[p]);
-                __threadfence();
-                epi_barrier();
+                epi_barrier();   // cta-scope happens-before from every writer to the releasing thread
                 if (threadIdx.x == 128) {
-                    const int t = atomicAdd(&my_tickets[rb], 1);
+                    int t;
+                    asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(t) : "l"(my_tickets + rb) : "memory");
                     misc[7] = (t == n_contrib - 1);
                     if (t == n_contrib - 1) my_tickets[rb] = 0;
                 }
                 epi_barrier();
                 do_finish = misc[7] != 0;
                 if (do_finish) {
-                    __threadfence();
 #pragma unroll
                     for (int p = 0; p < PARTS; ++p) {
                         float s = 0.0f;
@@ -301,6 +343,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
 
 // ------------------------------------------------------------------------------------------------ ops
 struct TcQkvOp {
+    static constexpr bool kBulkX = false;
     static constexpr int kParts = 1, kXParts = 1, kStages = 10;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;
@@ -353,6 +396,7 @@ struct TcQkvOp {
 };
 
 struct TcOProjOp {
+    static constexpr bool kBulkX = true;
     static constexpr int kParts = 1, kXParts = 1, kStages = 10;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* x;
@@ -362,7 +406,7 @@ struct TcOProjOp {
     __device__ int x_elems() const { return K; }
     __device__ int num_row_blocks() const { return (N + 127) / 128; }
     __device__ int a_row(int, int rb, int, const TcSmem&) const { return rb * 128; }
-    __device__ void prologue(int b, const TcSmem& sm) const { tc_load_x_copy(x + static_cast<long long>(b) * K, sm.xs, K); }
+    __device__ void prologue(int b, const TcSmem& sm) const { tc_bulk_x(x + static_cast<long long>(b) * K, sm.xs, K, sm.x_ready); }
     __device__ void finish(int b, int rb, int row, const float (&v)[1], TcFinish&, const TcSmem&) const {
         const int r = rb * 128 + row;
         if (r < N) {
@@ -374,6 +418,7 @@ struct TcOProjOp {
 };
 
 struct TcGateUpOp {
+    static constexpr bool kBulkX = false;
     static constexpr int kParts = 2, kXParts = 1, kStages = 5;
     static constexpr bool kRowsNeedPrologue = true, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;
@@ -397,9 +442,13 @@ struct TcGateUpOp {
         float part[9];
 #pragma unroll
         for (int e = 0; e < 9; ++e) part[e] = 0.0f;
+#pragma unroll 2
         for (int i = t * 8; i < K; i += 128 * 8) {
             const uint4 hv = *reinterpret_cast<const uint4*>(hr + i);
             const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w + i));
+            uint4 ge[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ge[e] = __ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * K + i));
             const uint32_t a[4] = {hv.x, hv.y, hv.z, hv.w}, gg[4] = {g.x, g.y, g.z, g.w};
             float xw[8];
 #pragma unroll
@@ -411,8 +460,7 @@ struct TcGateUpOp {
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const uint4 ge = __ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * K + i));
-                const uint32_t w[4] = {ge.x, ge.y, ge.z, ge.w};
+                const uint32_t w[4] = {ge[e].x, ge[e].y, ge[e].z, ge[e].w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) part[1 + e] += xw[2 * q] * bf16_lo(w[q]) + xw[2 * q + 1] * bf16_hi(w[q]);
             }
@@ -470,6 +518,7 @@ struct TcGateUpOp {
 };
 
 struct TcDownOp {
+    static constexpr bool kBulkX = true;
     static constexpr int kParts = 2, kXParts = 2, kStages = 4;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = true;
     const __nv_bfloat16* act;   // [B, 2, I]
@@ -484,7 +533,7 @@ struct TcDownOp {
     __device__ void prologue(int b, const TcSmem& sm) const {
         const int t = threadIdx.x - 128;
         if (t < 2) sm.prep[t] = topk_w[b * 2 + t];
-        tc_load_x_copy(act + static_cast<long long>(b) * 2 * K, sm.xs, 2 * K);
+        tc_bulk_x(act + static_cast<long long>(b) * 2 * K, sm.xs, 2 * K, sm.x_ready);
     }
     __device__ void finish(int b, int rb, int row, const float (&v)[2], TcFinish&, const TcSmem& sm) const {
         const int r = rb * 128 + row;
@@ -504,6 +553,7 @@ __device__ __forceinline__ unsigned long long tc_pack_argmax(float v, int idx) {
 }
 
 struct TcLmHeadOp {
+    static constexpr bool kBulkX = false;
     static constexpr int kParts = 1, kXParts = 1, kStages = 10;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;

@@ -331,12 +331,21 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
 
     const int n_sms = num_sms();
     const long long m_tiles_ub = (args.M / 128) + args.num_groups;  // valid for any ragged split of M rows
+    // Tile-shape choice.  Small-M problems stream each weight tile once and are HBM-bound, so what matters is how
+    // evenly the tiles fill the 148 SMs (wave quantisation); large-M problems want the 256-wide tile (smem operand
+    // bandwidth: 96 B/cycle/SM instead of 128).  Estimate the tile count and take the widest tile whose last wave
+    // is not mostly idle.
+    const long long m_tiles_est = (args.M + 127) / 128 + (args.num_groups > 1 ? args.num_groups / 2 : 0);
+    auto wave_eff = [&](int bn_out) {
+        const long long tiles = m_tiles_est * ((args.N + bn_out - 1) / bn_out);
+        const long long waves = (tiles + n_sms - 1) / n_sms;
+        return static_cast<double>(tiles) / static_cast<double>(waves * n_sms);
+    };
     int block_n;
     if (silu) {
-        block_n = 256;
+        block_n = (wave_eff(128) + 0.04 >= wave_eff(64)) ? 256 : 128;   // output widths 128 / 64
     } else {
-        const long long tiles256 = m_tiles_ub * ((args.N + 255) / 256);
-        block_n = (tiles256 >= n_sms && args.N >= 256) ? 256 : 128;
+        block_n = (args.N >= 256 && wave_eff(256) + 0.04 >= wave_eff(128)) ? 256 : 128;
     }
     const int bn_out = silu ? block_n / 2 : block_n;
     const long long max_tiles_ll = m_tiles_ub * ((args.N + bn_out - 1) / bn_out);
@@ -359,7 +368,8 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
         int rc = make_tensor_map_bf16(&tmB, B, 3, dims, strides, box, true);
         if (rc) return rc;
     }
-    if (silu) return launch_gemm<256, true, 4>(tmA, tmB, args, max_tiles, stream);
+    if (silu && block_n == 256) return launch_gemm<256, true, 4>(tmA, tmB, args, max_tiles, stream);
+    if (silu) return launch_gemm<128, true, 6>(tmA, tmB, args, max_tiles, stream);
     if (block_n == 256) return launch_gemm<256, false, 4>(tmA, tmB, args, max_tiles, stream);
     return launch_gemm<128, false, 6>(tmA, tmB, args, max_tiles, stream);
 }
