@@ -246,21 +246,53 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
     } else if (warp == 3) {
         // ---------------------------------------------------------------- x-tile writer
         // per stage: copy 128 B of the activation vector into row 0 of the N tile
-        mbar_wait(x_ready, 0, 25);
         int stage = 0;
         uint32_t phase = 0;
-        for (long long u = u0; u < u1; ++u) {
-            const int kb = static_cast<int>(u % n_kb);
-            mbar_wait(&empty_bar[stage], phase ^ 1, 26);
-            if (lane < 8 * XPARTS) {
-                const int px = lane >> 3, c = lane & 7;
-                *reinterpret_cast<uint4*>(sX + stage * STAGE_X + px * TC_X_BYTES + c * 16) =
-                    *reinterpret_cast<const uint4*>(xs + static_cast<long long>(px) * K + kb * 64 + c * 8);
+        if constexpr (Op::kXFromGlobal) {
+            // the vectors stay in L2; this warp keeps the chunks of the next LOOK units in registers
+            constexpr int LOOK = 4;
+            pdl_wait();
+            const __nv_bfloat16* xg = op.x_global(b);
+            const int px = lane >> 3, c = lane & 7;
+            const bool active = lane < 8 * XPARTS;
+            uint4 nxt[LOOK];
+#pragma unroll
+            for (int j = 0; j < LOOK; ++j)
+                if (active && u0 + j < u1)
+                    nxt[j] = *reinterpret_cast<const uint4*>(xg + static_cast<long long>(px) * K + ((u0 + j) % n_kb) * 64 + c * 8);
+            for (long long u = u0; u < u1; u += LOOK) {
+#pragma unroll
+                for (int j = 0; j < LOOK; ++j) {
+                    if (u + j < u1) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, 26);
+                        if (active) {
+                            *reinterpret_cast<uint4*>(sX + stage * STAGE_X + px * TC_X_BYTES + c * 16) = nxt[j];
+                            if (u + j + LOOK < u1)
+                                nxt[j] = *reinterpret_cast<const uint4*>(xg + static_cast<long long>(px) * K +
+                                                                         ((u + j + LOOK) % n_kb) * 64 + c * 8);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        } else {
+            mbar_wait(x_ready, 0, 25);
+            for (long long u = u0; u < u1; ++u) {
+                const int kb = static_cast<int>(u % n_kb);
+                mbar_wait(&empty_bar[stage], phase ^ 1, 26);
+                if (lane < 8 * XPARTS) {
+                    const int px = lane >> 3, c = lane & 7;
+                    *reinterpret_cast<uint4*>(sX + stage * STAGE_X + px * TC_X_BYTES + c * 16) =
+                        *reinterpret_cast<const uint4*>(xs + static_cast<long long>(px) * K + kb * 64 + c * 8);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- prologue + epilogue (128 threads)
@@ -343,8 +375,10 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
 
 // ------------------------------------------------------------------------------------------------ ops
 struct TcQkvOp {
+    __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
+    static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
-    static constexpr int kParts = 1, kXParts = 1, kStages = 10;
+    static constexpr int kParts = 1, kXParts = 1, kStages = 5;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;
     const __nv_bfloat16* norm_w;
@@ -396,8 +430,10 @@ struct TcQkvOp {
 };
 
 struct TcOProjOp {
+    __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
+    static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = true;
-    static constexpr int kParts = 1, kXParts = 1, kStages = 10;
+    static constexpr int kParts = 1, kXParts = 1, kStages = 5;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* x;
     __nv_bfloat16* h;
@@ -418,8 +454,10 @@ struct TcOProjOp {
 };
 
 struct TcGateUpOp {
+    __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
+    static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
-    static constexpr int kParts = 2, kXParts = 1, kStages = 5;
+    static constexpr int kParts = 2, kXParts = 1, kStages = 3;
     static constexpr bool kRowsNeedPrologue = true, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;
     const __nv_bfloat16* norm_w;
@@ -518,8 +556,9 @@ struct TcGateUpOp {
 };
 
 struct TcDownOp {
-    static constexpr bool kBulkX = true;
-    static constexpr int kParts = 2, kXParts = 2, kStages = 4;
+    static constexpr bool kXFromGlobal = true;
+    static constexpr bool kBulkX = false;
+    static constexpr int kParts = 2, kXParts = 2, kStages = 3;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = true;
     const __nv_bfloat16* act;   // [B, 2, I]
     const int* topk_ids;
@@ -527,13 +566,13 @@ struct TcDownOp {
     __nv_bfloat16* h;
     int K, H;                   // K = I
 
-    __device__ int x_elems() const { return 2 * K; }
+    __device__ int x_elems() const { return 0; }   // the activation vectors are streamed from L2 by the x-tile writer
+    __device__ const __nv_bfloat16* x_global(int b) const { return act + static_cast<long long>(b) * 2 * K; }
     __device__ int num_row_blocks() const { return (H + 127) / 128; }
     __device__ int a_row(int b, int rb, int p, const TcSmem&) const { return topk_ids[b * 2 + p] * H + rb * 128; }
     __device__ void prologue(int b, const TcSmem& sm) const {
         const int t = threadIdx.x - 128;
         if (t < 2) sm.prep[t] = topk_w[b * 2 + t];
-        tc_bulk_x(act + static_cast<long long>(b) * 2 * K, sm.xs, 2 * K, sm.x_ready);
     }
     __device__ void finish(int b, int rb, int row, const float (&v)[2], TcFinish&, const TcSmem& sm) const {
         const int r = rb * 128 + row;
@@ -553,8 +592,10 @@ __device__ __forceinline__ unsigned long long tc_pack_argmax(float v, int idx) {
 }
 
 struct TcLmHeadOp {
+    __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
+    static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
-    static constexpr int kParts = 1, kXParts = 1, kStages = 10;
+    static constexpr int kParts = 1, kXParts = 1, kStages = 5;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;
     long long h_stride;
@@ -697,7 +738,7 @@ extern "C" int vita_decode_tc_moe_down(const void* act, const void* w2, const in
     VITA_REQUIRE(workspace && n_rb <= ws_row_blocks, "workspace too small");
     if (B == 0) return VITA_OK;
     TcDownOp op{BF16C(act), topk_ids, topk_w, static_cast<__nv_bfloat16*>(h), (int)I, (int)H};
-    return launch_tc(op, w2, E * H, (int)I, n_rb, (int)(2 * I), (int)B, split_ws(workspace, B, ws_row_blocks),
+    return launch_tc(op, w2, E * H, (int)I, n_rb, 0, (int)B, split_ws(workspace, B, ws_row_blocks),
                      static_cast<cudaStream_t>(stream), "decode_tc_moe_down");
 }
 

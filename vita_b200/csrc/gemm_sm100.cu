@@ -14,6 +14,8 @@
 //   vita/model/multimodal_encoder/whale/module/layer/attention.py:371-373,381,419 ; :145-147
 //   vita/model/multimodal_projector/builder.py:164-168
 //   transformers MixtralAttention q/k/v/o_proj, MixtralExperts.forward (gate_up_proj / down_proj)
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -342,8 +344,14 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
         return static_cast<double>(tiles) / static_cast<double>(waves * n_sms);
     };
     int block_n;
-    if (silu) {
-        block_n = (wave_eff(128) + 0.04 >= wave_eff(64)) ? 256 : 128;   // output widths 128 / 64
+    const char* force = getenv("VITA_B200_GEMM_BN");   // tuning aid: force the tile width (128 / 256)
+    if (force && (atoi(force) == 128 || atoi(force) == 256)) {
+        block_n = atoi(force);
+        if (!silu && args.N < 256) block_n = 128;
+    } else if (silu) {
+        // the 64-wide variant halves the weight tile but re-reads the activation tile twice as often from L2:
+        // measured slower (474 vs 388 us per layer at S=506), so it is only used when forced
+        block_n = 256;
     } else {
         block_n = (args.N >= 256 && wave_eff(256) + 0.04 >= wave_eff(128)) ? 256 : 128;
     }
