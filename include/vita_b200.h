@@ -106,6 +106,11 @@ int vita_moe_gemm_down(const void* Act, const void* W_down, void* Y_perm, const 
 int vita_moe_combine(void* h, const void* y_perm, const int32_t* perm_row, const void* next_norm_w, void* xn_out,
                      int64_t n_tok, int64_t H, float eps, void* stream);
 
+/* expert-parallel tail of a decoder layer: h += y where y is the all-reduced sum of the ranks' partial MoE outputs
+ * (each rank ran vita_moe_combine on a zeroed buffer with only its local experts' rows filled); optional next RMSNorm. */
+int vita_add_rmsnorm(void* h, const void* y, const void* next_norm_w, void* xn_out, int64_t n_tok, int64_t H, float eps,
+                     void* stream);
+
 /* ---- InternViT front / back end --------------------------------------------------------------------------- */
 /* im2col for Conv2d(3,1024,k=14,s=14) (modeling_intern_vit.py:80-85,109): out [n_img*(HW/P)^2, k_pad]. */
 int vita_vit_im2col(const void* images, void* out, int64_t n_img, int64_t C, int64_t HW, int64_t P, int64_t k_pad,

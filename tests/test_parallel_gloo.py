@@ -51,3 +51,46 @@ def test_single_process_degenerates():
     assert parallel.shard_requests(3, 0, 1) == [0, 1, 2]
     assert parallel.reduce_max(3.5) == 3.5
     assert parallel.gather_token_lists([[1], [2, 3]], [0, 1], 2) == [[1], [2, 3]]
+
+
+def _ep_worker(rank, world, port, q):
+    """Expert-parallel decomposition of the MoE block: sum over ranks of the local experts' weighted outputs
+    (what MixtralDecoder.prefill all-reduces) equals the full MixtralSparseMoeBlock of the oracle."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    import torch.nn.functional as F
+    from oracle import vita_oracle as O
+    from vita_b200 import parallel, weights as W
+    from vita_b200.config import VitaConfig
+    parallel.init("gloo")
+    cfg = VitaConfig.tiny()
+    state = W.synthetic_state(cfg, 0, parts=("llm",))
+    lo, hi = W.expert_range(cfg.llm.num_local_experts, rank, world)
+    xn = torch.randn(37, cfg.llm.hidden_size, generator=torch.Generator().manual_seed(5))
+    full, top_i, top_v = O.sparse_moe(state, cfg.llm, 0, xn)
+    part = torch.zeros_like(xn)
+    for e in range(lo, hi):
+        tok, kpos = torch.where(top_i == e)
+        if tok.numel():
+            w1, w3, w2 = O.expert_weights(state, cfg.llm, 0, e)
+            y = O.linear(F.silu(O.linear(xn[tok], w1)) * O.linear(xn[tok], w3), w2) * top_v[tok, kpos, None]
+            part.index_add_(0, tok, y)
+    torch.distributed.all_reduce(part)
+    q.put((rank, (lo, hi), float((part - full).abs().max())))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_expert_parallel_decomposition_two_ranks():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ep_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [(0, 4), (4, 8)]
+    assert all(r[2] < 1e-5 for r in res)

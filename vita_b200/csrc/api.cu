@@ -41,7 +41,7 @@ bool use_pdl() {
     static int cached = -1;
     if (cached < 0) {
         const char* e = getenv("VITA_B200_PDL");
-        cached = (e == nullptr || e[0] != '0') ? 1 : 0;
+        cached = (e != nullptr && e[0] == '1') ? 1 : 0;   // measured: no gain (5.27 ms/token off vs 5.31 on) -> opt-in
     }
     return cached == 1;
 }

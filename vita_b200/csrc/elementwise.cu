@@ -208,6 +208,7 @@ rmsnorm_router_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* 
     const uint4* hr = reinterpret_cast<const uint4*>(h + static_cast<long long>(tok) * H);
     const int nvec = H >> 3;
     float ss = 0.0f;
+#pragma unroll 4
     for (int i = lane; i < nvec; i += 32) {
         float f[8];
         unpack8(hr[i], f);
@@ -221,6 +222,7 @@ rmsnorm_router_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* 
     for (int e = 0; e < E; ++e) logit[e] = 0.0f;
     uint4* xr = reinterpret_cast<uint4*>(xn + static_cast<long long>(tok) * H);
     const uint4* nw = reinterpret_cast<const uint4*>(norm_w);
+#pragma unroll 2
     for (int i = lane; i < nvec; i += 32) {
         float f[8], g[8];
         unpack8(hr[i], f);
@@ -333,6 +335,53 @@ moe_combine_kernel(__nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restric
             unpack8(y1[idx], c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = a[j] + (b[j] + c[j]);
+            v[i] = pack8(a);
+            hr[idx] = v[i];
+            unpack8(v[i], a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss += a[j] * a[j];
+        }
+    }
+    if (next_norm_w == nullptr) return;
+    const float tot = block_sum<THREADS>(ss, red);
+    const float inv = rsqrtf(tot / static_cast<float>(H) + eps);
+    const uint4* wr = reinterpret_cast<const uint4*>(next_norm_w);
+    uint4* xr = reinterpret_cast<uint4*>(xn_out + tok * H);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int idx = threadIdx.x + i * THREADS;
+        if (idx < nvec) {
+            float f[8], g[8];
+            unpack8(v[i], f);
+            unpack8(__ldg(wr + idx), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = f[j] * inv * g[j];
+            xr[idx] = pack8(f);
+        }
+    }
+}
+
+// h += y (expert-parallel: y is the all-reduced MoE output), optionally followed by the next RMSNorm.
+template <int THREADS, int VPT>
+__global__ void __launch_bounds__(THREADS)
+add_rmsnorm_kernel(__nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ y,
+                   const __nv_bfloat16* __restrict__ next_norm_w, __nv_bfloat16* __restrict__ xn_out, int H, float eps) {
+    __shared__ float red[32];
+    const long long tok = blockIdx.x;
+    const int nvec = H >> 3;
+    uint4* hr = reinterpret_cast<uint4*>(h + tok * H);
+    const uint4* yr = reinterpret_cast<const uint4*>(y + tok * H);
+    uint4 v[VPT];
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int idx = threadIdx.x + i * THREADS;
+        if (idx < nvec) {
+            float a[8], b[8];
+            unpack8(hr[idx], a);
+            unpack8(yr[idx], b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += b[j];
             v[i] = pack8(a);
             hr[idx] = v[i];
             unpack8(v[i], a);
@@ -583,8 +632,8 @@ extern "C" int vita_moe_router(const void* h, const void* norm_w, const void* ga
     VITA_REQUIRE(E == 8, "router is specialised for 8 experts (Mixtral-8x7B)");
     VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
     if (n_tok == 0) return VITA_OK;
-    const unsigned grid = static_cast<unsigned>((n_tok + 7) / 8);
-    rmsnorm_router_kernel<8><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const unsigned grid = static_cast<unsigned>((n_tok + 3) / 4);
+    rmsnorm_router_kernel<8><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         BF(h), BF(norm_w), BF(gate_w), BFM(xn), topk_ids, topk_w, (int)n_tok, (int)H, eps);
     return check_launch("moe_router");
 }
@@ -605,6 +654,15 @@ extern "C" int vita_moe_combine(void* h, const void* y_perm, const int32_t* perm
     moe_combine_kernel<256, 2><<<static_cast<unsigned>(n_tok), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         BFM(h), BF(y_perm), perm_row, BF(next_norm_w), BFM(xn_out), (int)H, eps);
     return check_launch("moe_combine");
+}
+
+extern "C" int vita_add_rmsnorm(void* h, const void* y, const void* next_norm_w, void* xn_out, int64_t n_tok, int64_t H,
+                                float eps, void* stream) {
+    VITA_REQUIRE(H % 8 == 0 && H <= 8 * 2 * 256, "H must be a multiple of 8 and <= 4096");
+    if (n_tok == 0) return VITA_OK;
+    add_rmsnorm_kernel<256, 2><<<static_cast<unsigned>(n_tok), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        BFM(h), BF(y), BF(next_norm_w), BFM(xn_out), (int)H, eps);
+    return check_launch("add_rmsnorm");
 }
 
 extern "C" int vita_vit_im2col(const void* images, void* out, int64_t n_img, int64_t C, int64_t HW, int64_t P,

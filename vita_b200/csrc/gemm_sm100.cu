@@ -352,8 +352,12 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
         // the 64-wide variant halves the weight tile but re-reads the activation tile twice as often from L2:
         // measured slower (474 vs 388 us per layer at S=506), so it is only used when forced
         block_n = 256;
+    } else if (args.N < 256) {
+        block_n = 128;
+    } else if (m_tiles_est * ((args.N + 255) / 256) >= 2 * n_sms) {
+        block_n = 256;   // many tiles: compute-bound, the wide tile wins (measured 1234 vs 891 TFLOP/s at M=4096)
     } else {
-        block_n = (args.N >= 256 && wave_eff(256) + 0.04 >= wave_eff(128)) ? 256 : 128;
+        block_n = (wave_eff(256) + 0.04 >= wave_eff(128)) ? 256 : 128;
     }
     const int bn_out = silu ? block_n / 2 : block_n;
     const long long max_tiles_ll = m_tiles_ub * ((args.N + bn_out - 1) / bn_out);

@@ -82,6 +82,12 @@ class MixtralDecoder:
         self._graph = None
         self._graph_batch = None
         self._prefill_ws = {}
+        # expert parallelism: this rank holds experts [e_lo, e_hi) of every layer; attention, router, embeddings and
+        # the KV cache are replicated, the partial MoE outputs are summed with one all-reduce per layer
+        self.ep_rank, self.ep_world = weights.get("ep", (0, 1))
+        per = cfg.num_local_experts // self.ep_world
+        self.e_lo, self.e_hi = self.ep_rank * per, (self.ep_rank + 1) * per
+        assert weights["layers"][0]["w13"].shape[0] == per, "expert tensors do not match the EP layout"
 
     # ------------------------------------------------------------------------------------------ prefill
     def _ws(self, S: int):
@@ -106,6 +112,7 @@ class MixtralDecoder:
                 xp=torch.empty(cap * 2, H, dtype=BF16, device=dev),
                 act=torch.empty(cap * 2, I, dtype=BF16, device=dev),
                 yp=torch.empty(cap * 2, H, dtype=BF16, device=dev),
+                ybuf=torch.empty(cap, H, dtype=BF16, device=dev) if self.ep_world > 1 else None,
                 pos=torch.arange(cap, dtype=torch.int32, device=dev))
         return self._prefill_ws
 
@@ -141,10 +148,23 @@ class MixtralDecoder:
             ops.moe_router(h, lw["ln2"], lw["gate"], xn2, ids, tw, c.rms_norm_eps)
             ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, S, E)
             ops.row_copy(xn2, rtok, None, xp, 2 * S)
-            ops.moe_gate_up(xp, lw["w13"], act, ws["offs"], 2 * S)
-            ops.moe_down(act, lw["w2"], yp, ws["offs"], rw, 2 * S)
             nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else (w["norm"] if all_logits else None)
-            ops.moe_combine(h, yp, perm, nxt, xn if nxt is not None else None, c.rms_norm_eps)
+            if self.ep_world == 1:
+                ops.moe_gate_up(xp, lw["w13"], act, ws["offs"], 2 * S)
+                ops.moe_down(act, lw["w2"], yp, ws["offs"], rw, 2 * S)
+                ops.moe_combine(h, yp, perm, nxt, xn if nxt is not None else None, c.rms_norm_eps)
+            else:
+                # local experts only: the grouped GEMMs walk offs[e_lo : e_hi + 1]; rows of remote experts stay zero
+                import torch.distributed as dist
+                offs_local = ws["offs"][self.e_lo:]
+                yp.zero_()
+                ops.moe_gate_up(xp, lw["w13"], act, offs_local, 2 * S)
+                ops.moe_down(act, lw["w2"], yp, offs_local, rw, 2 * S)
+                ybuf = ws["ybuf"][:S]
+                ybuf.zero_()
+                ops.moe_combine(ybuf, yp, perm, None, None, c.rms_norm_eps)       # partial sum of the local experts
+                dist.all_reduce(ybuf)                                              # NCCL over NVLink (sum, bf16)
+                ops.add_rmsnorm(h, ybuf, nxt, xn if nxt is not None else None, c.rms_norm_eps)
         self.cache.cache_len[slot:slot + 1] += S
         # first generated token: final norm + lm_head + arg-max on the last row only
         self.best[slot:slot + 1].zero_()
@@ -200,6 +220,10 @@ class MixtralDecoder:
 
     @torch.no_grad()
     def decode_step(self, B: int = 1, use_graph: bool = True, want_logits: bool = False):
+        assert self.ep_world == 1, "expert-parallel mode covers the prefill (BASELINE configs[3]); decode is replicated"
+        self._decode_step(B, use_graph, want_logits)
+
+    def _decode_step(self, B: int = 1, use_graph: bool = True, want_logits: bool = False):
         """Generate one token for batch slots [0, B): consumes self.best, appends to token_log, leaves the next
         arg-max in self.best.  With use_graph the whole step (2 + 5 * layers kernels) replays as one CUDA graph."""
         if not use_graph:

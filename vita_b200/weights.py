@@ -178,8 +178,9 @@ def rope_table(max_pos: int, head_dim: int, theta: float) -> torch.Tensor:
     return torch.stack([freqs.cos(), freqs.sin()], dim=1).contiguous()
 
 
-def pack_llm(state, cfg: VitaConfig, device) -> dict:
+def pack_llm(state, cfg: VitaConfig, device, ep=None) -> dict:
     c = cfg.llm
+    e_lo, e_hi = (0, c.num_local_experts) if ep is None else expert_range(c.num_local_experts, ep[0], ep[1])
     dev = lambda t: t.to(device=device, dtype=BF16).contiguous()
     out = {"embed": dev(state["model.embed_tokens.weight"]), "norm": dev(state["model.norm.weight"]),
            "lm_head": dev(state["lm_head.weight"]), "layers": []}
@@ -187,10 +188,10 @@ def pack_llm(state, cfg: VitaConfig, device) -> dict:
         p = f"model.layers.{l}."
         moe = "block_sparse_moe." if (p + "block_sparse_moe.gate.weight") in state else "mlp."
         if (p + moe + "experts.gate_up_proj") in state:           # transformers >= 5 naming
-            w13 = state[p + moe + "experts.gate_up_proj"]
-            w2 = state[p + moe + "experts.down_proj"]
+            w13 = state[p + moe + "experts.gate_up_proj"][e_lo:e_hi]
+            w2 = state[p + moe + "experts.down_proj"][e_lo:e_hi]
         else:
-            ex = [p + moe + f"experts.{e}." for e in range(c.num_local_experts)]
+            ex = [p + moe + f"experts.{e}." for e in range(e_lo, e_hi)]
             w13 = torch.stack([torch.cat([state[q + "w1.weight"], state[q + "w3.weight"]], dim=0) for q in ex])
             w2 = torch.stack([state[q + "w2.weight"] for q in ex])
         out["layers"].append({
@@ -203,6 +204,7 @@ def pack_llm(state, cfg: VitaConfig, device) -> dict:
             "w13": dev(w13), "w2": dev(w2)})
     out["rope"] = rope_table(min(c.max_position_embeddings, max(c.tokenizer_model_max_length + 1024, 2048)),
                              c.head_dim, c.rope_theta).to(device)
+    out["ep"] = (0, 1) if ep is None else tuple(ep)
     return out
 
 
@@ -294,33 +296,52 @@ def pack(state, cfg: VitaConfig, device) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------ on-device random
-def random_packed(cfg: VitaConfig, device, seed: int = 0, parts=("llm", "vision", "projector", "audio")) -> dict:
-    """Packed weights with the same shapes/statistics as pack(synthetic_state()), drawn on the GPU (bench only)."""
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
+def expert_range(num_experts: int, rank: int, world: int):
+    """Contiguous expert ownership for expert parallelism: rank r owns experts [lo, hi)."""
+    assert num_experts % world == 0, "the number of experts must be divisible by the EP world size"
+    per = num_experts // world
+    return rank * per, (rank + 1) * per
 
-    def fill(tree):
+
+def random_packed(cfg: VitaConfig, device, seed: int = 0, parts=("llm", "vision", "projector", "audio"), ep=None) -> dict:
+    """Packed weights with the same shapes/statistics as pack(synthetic_state()), drawn on the GPU (bench only).
+
+    Every tensor (and every expert of the stacked expert tensors) has its own generator seed derived from
+    (seed, name), so a rank that holds only experts [lo, hi) (`ep=(rank, world)`) gets exactly the values the
+    single-GPU model has for them, and all ranks agree on the replicated tensors."""
+    g = torch.Generator(device=device)
+
+    def draw(name, shape, kind):
+        g.manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63 - 1))
+        if kind == "gain":
+            return (1.0 + 0.1 * torch.randn(shape, device=device, generator=g)).to(BF16)
+        if kind == "ls":
+            return (0.5 + 0.05 * torch.randn(shape, device=device, generator=g)).to(BF16)
+        return torch.empty(shape, device=device, dtype=BF16).normal_(0.0, 0.02, generator=g)
+
+    def fill(tree, prefix):
         for k, v in (tree.items() if isinstance(tree, dict) else enumerate(tree)):
+            name = f"{prefix}.{k}"
             if isinstance(v, (dict, list)):
-                fill(v)
+                fill(v, name)
             elif isinstance(v, tuple):
                 shape, kind = v
-                if kind == "gain":
-                    t = 1.0 + 0.1 * torch.randn(shape, device=device, generator=g)
-                elif kind == "ls":
-                    t = 0.5 + 0.05 * torch.randn(shape, device=device, generator=g)
+                if kind == "experts":                       # stacked [E_local, rows, cols], one seed per expert
+                    lo, hi, rows, cols = shape
+                    tree[k] = torch.stack([draw(f"{name}.{e}", (rows, cols), "m") for e in range(lo, hi)])
                 else:
-                    t = torch.empty(shape, device=device, dtype=BF16).normal_(0.0, 0.02, generator=g)
-                tree[k] = t.to(BF16)
+                    tree[k] = draw(name, shape, kind)
 
     c, v, a = cfg.llm, cfg.vision, cfg.audio
     H, I, E = c.hidden_size, c.intermediate_size, c.num_local_experts
+    lo, hi = (0, E) if ep is None else expert_range(E, ep[0], ep[1])
     out = {}
     if "llm" in parts:
         out["llm"] = {"embed": ((c.vocab_size, H), "m"), "norm": ((H,), "gain"), "lm_head": ((c.vocab_size, H), "m"),
                       "layers": [{"ln1": ((H,), "gain"), "wqkv": ((c.qkv_rows, H), "m"),
                                   "wo": ((H, c.num_attention_heads * c.head_dim), "m"), "ln2": ((H,), "gain"),
-                                  "gate": ((E, H), "m"), "w13": ((E, 2 * I, H), "m"), "w2": ((E, H, I), "m")}
+                                  "gate": ((E, H), "m"), "w13": ((lo, hi, 2 * I, H), "experts"),
+                                  "w2": ((lo, hi, H, I), "experts")}
                                  for _ in range(c.num_hidden_layers)]}
     if "vision" in parts:
         VH, VM = v.hidden_size, v.intermediate_size
@@ -347,10 +368,11 @@ def random_packed(cfg: VitaConfig, device, seed: int = 0, parts=("llm", "vision"
                                     "ln2_w": ((C,), "gain"), "ln2_b": ((C,), "m"), "w1": ((a.linear_units, C), "m"),
                                     "b1": ((a.linear_units,), "m"), "w2": ((C, a.linear_units), "m"),
                                     "b2": ((C,), "m")} for _ in range(a.num_blocks)]}
-    fill(out)
+    fill(out, "w")
     if "llm" in out:
         out["llm"]["rope"] = rope_table(min(c.max_position_embeddings, max(c.tokenizer_model_max_length + 1024, 2048)),
                                         c.head_dim, c.rope_theta).to(device)
+        out["llm"]["ep"] = (0, 1) if ep is None else tuple(ep)
     if "audio" in out:
         out["audio"]["cmvn_mean"] = torch.zeros(a.input_dim, device=device)
         out["audio"]["cmvn_istd"] = torch.ones(a.input_dim, device=device)
