@@ -186,6 +186,25 @@ int vita_tc_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, 
                            uint64_t* best, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H, int64_t V,
                            float eps, void* stream);
 
+/* ---- single-kernel decode step (bs = 1) -------------------------------------------------------------------
+ * All linears of all layers, the paged attention and the LM head as phases of ONE persistent launch separated by
+ * grid barriers (decode_mega.cu): the TMA producer streams the next phase's weights while the epilogue warps cross
+ * the barrier.  vita_mega_build writes the device-resident tensor maps / per-layer pointer table once;
+ * vita_mega_decode_step runs one token (precede it with vita_decode_embed and zero `grid_bar`). */
+int64_t vita_mega_maps_bytes(int64_t n_layers);
+int64_t vita_mega_layers_bytes(int64_t n_layers);
+int64_t vita_mega_workspace_floats(int64_t max_row_blocks);
+int vita_mega_build(void* maps_out, void* layers_out, int64_t n_layers, const void* const* wqkv, const void* const* wo,
+                    const void* const* w13, const void* const* w2, const void* const* ln1, const void* const* ln2,
+                    const void* const* gate, void* const* k_cache, void* const* v_cache, const void* lm_head, int64_t H,
+                    int64_t I, int64_t E, int64_t n_q, int64_t n_kv, int64_t V);
+int vita_mega_decode_step(const void* maps, const void* layers, int64_t n_layers, const void* final_norm, void* h,
+                          void* q, void* attn, void* act, void* logits, uint64_t* best, const float* cos_sin,
+                          const int32_t* cur_pos, const int32_t* block_table, float* scratch, int32_t* tickets,
+                          uint32_t* grid_bar, float* attn_part_o, float* attn_part_ml, int32_t* attn_tickets, int64_t H,
+                          int64_t I, int64_t n_q, int64_t n_kv, int64_t V, int64_t page_size, int64_t max_pages,
+                          int64_t splits, float eps, float attn_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

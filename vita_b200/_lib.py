@@ -55,6 +55,12 @@ SIGNATURES = {
     "vita_decode_tc_moe_gate_up": (c_int, [P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, c_float, P]),
     "vita_decode_tc_moe_down": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, I64, P]),
     "vita_tc_lm_head_argmax": (c_int, [P, I64, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
+    "vita_mega_maps_bytes": (I64, [I64]),
+    "vita_mega_layers_bytes": (I64, [I64]),
+    "vita_mega_workspace_floats": (I64, [I64]),
+    "vita_mega_build": (c_int, [P, P, I64, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64]),
+    "vita_mega_decode_step": (c_int, [P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64,
+                                      I64, I64, I64, c_float, c_float, P]),
 }
 
 

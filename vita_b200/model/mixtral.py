@@ -79,6 +79,12 @@ class MixtralDecoder:
         max_rb = max((cfg.vocab_size + 127) // 128, 2 * (I // 128), cfg.num_attention_heads
                      + 2 * cfg.num_key_value_heads, (H + 127) // 128)
         self.tc_ws = ops.TcWorkspace(B, max_rb, dev) if self.use_tc else None
+        # single-kernel decode step (bs = 1): VITA_B200_DECODE=mega
+        self.mega = None
+        if os.environ.get("VITA_B200_DECODE", "kernels") == "mega" and self.use_tc and weights.get("ep", (0, 1))[1] == 1:
+            self.mega = ops.MegaDecode(weights["layers"], weights["lm_head"], self.cache.k, self.cache.v, H, I,
+                                       cfg.num_local_experts, cfg.num_attention_heads, cfg.num_key_value_heads,
+                                       cfg.vocab_size, decode_splits, dev)
         self._graph = None
         self._graph_batch = None
         self._prefill_ws = {}
@@ -186,6 +192,11 @@ class MixtralDecoder:
         h = self.d_h[:B]
         ops.decode_embed(self.best[:B], self.token_log[:B], self.gen_count[:B], cache.cache_len[:B], cache.cur_pos[:B],
                          w["embed"], h)
+        if self.mega is not None and B == 1:
+            self.mega.step(w["norm"], h, self.d_q[:1], self.d_attn[:1], self.d_act[:1],
+                           self.d_logits[:1] if want_logits else None, self.best[:1], w["rope"], cache.cur_pos[:1],
+                           cache.block_table[:1], cache.page_size, c.rms_norm_eps, D ** -0.5)
+            return
         tc, ws = self.use_tc, self.tc_ws
         for li, lw in enumerate(w["layers"]):
             if tc:
@@ -216,7 +227,7 @@ class MixtralDecoder:
 
     @property
     def launches_per_decode_step(self) -> int:
-        return 2 + 5 * self.cfg.num_hidden_layers
+        return 2 if self.mega is not None else 2 + 5 * self.cfg.num_hidden_layers
 
     @torch.no_grad()
     def decode_step(self, B: int = 1, use_graph: bool = True, want_logits: bool = False):

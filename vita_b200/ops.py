@@ -308,5 +308,37 @@ def tc_lm_head_argmax(h, h_stride, norm_w, w, logits, best, B, ws, eps):
               ws.max_row_blocks, B, H, V, float(eps), _stream())
 
 
+# ------------------------------------------------------------------------------------------------ single-kernel decode
+class MegaDecode:
+    """Device-resident tensor maps / layer table + workspaces of the single-kernel decode step (bs = 1)."""
+
+    def __init__(self, layers, lm_head, k_caches, v_caches, H, I, E, n_q, n_kv, V, splits, device):
+        lib = _lib.load()
+        L = len(layers)
+        self.L, self.H, self.I, self.n_q, self.n_kv, self.V, self.splits = L, H, I, n_q, n_kv, V, splits
+        self.maps = torch.zeros(lib.vita_mega_maps_bytes(L) + 64, dtype=torch.uint8, device=device)
+        self.layers = torch.zeros(lib.vita_mega_layers_bytes(L), dtype=torch.uint8, device=device)
+        arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
+        _lib.call("vita_mega_build", _p(self.maps), _p(self.layers), L, arr([l["wqkv"] for l in layers]),
+                  arr([l["wo"] for l in layers]), arr([l["w13"] for l in layers]), arr([l["w2"] for l in layers]),
+                  arr([l["ln1"] for l in layers]), arr([l["ln2"] for l in layers]), arr([l["gate"] for l in layers]),
+                  arr(k_caches), arr(v_caches), _p(lm_head), H, I, E, n_q, n_kv, V)
+        max_rb = max((V + 127) // 128, 2 * (I // 128), n_q + 2 * n_kv, (H + 127) // 128)
+        self.scratch = torch.zeros(lib.vita_mega_workspace_floats(max_rb), dtype=torch.float32, device=device)
+        self.tickets = torch.zeros(max_rb, dtype=torch.int32, device=device)
+        self.grid_bar = torch.zeros(1, dtype=torch.int32, device=device)
+        self.attn_part_o = torch.zeros(n_kv * splits * 4 * 128, dtype=torch.float32, device=device)
+        self.attn_part_ml = torch.zeros(n_kv * splits * 4 * 2, dtype=torch.float32, device=device)
+        self.attn_tickets = torch.zeros(n_kv, dtype=torch.int32, device=device)
+
+    def step(self, final_norm, h, q, attn, act, logits, best, cos_sin, cur_pos, block_table, page_size, eps, scale):
+        self.grid_bar.zero_()
+        _lib.call("vita_mega_decode_step", _p(self.maps), _p(self.layers), self.L, _p(final_norm), _p(h), _p(q),
+                  _p(attn), _p(act), _p(logits), _p(best), _p(cos_sin), _p(cur_pos), _p(block_table), _p(self.scratch),
+                  _p(self.tickets), _p(self.grid_bar), _p(self.attn_part_o), _p(self.attn_part_ml),
+                  _p(self.attn_tickets), self.H, self.I, self.n_q, self.n_kv, self.V, page_size, block_table.shape[1],
+                  self.splits, float(eps), float(scale), _stream())
+
+
 def launch_count(reset: bool = False) -> int:
     return int(_lib.load().vita_launch_count(1 if reset else 0))
