@@ -256,7 +256,9 @@ def run_b200(args):
     cfg = VitaConfig.full(args.layers)
     NT = args.new_tokens
     packed = W.random_packed(cfg, dev, seed=rank)
-    model = VITAMixtralForCausalLM(cfg, packed, dev, max_batch=1, max_seq_len=spliced_len(cfg) + NT + 64,
+    S_LONG = 4096   # BASELINE configs[3] sequence length: single-GPU prefill-only measurement (tensor-core roofline)
+    model = VITAMixtralForCausalLM(cfg, packed, dev, max_batch=1,
+                                   max_seq_len=max(spliced_len(cfg) + NT + 64, 0 if args.no_long_prefill else S_LONG + 64),
                                    max_new_tokens=NT + 16)
     ids, images_h, feats_h, lengths = make_inputs(cfg, seed=rank)
     images_d, feats_d = images_h.to(dev), feats_h.to(dev)
@@ -326,6 +328,23 @@ def run_b200(args):
     assert out.sequences.shape[1] == TEXT_TOKENS + NT
     barrier()
 
+    # ---- long prefill (S = 4096): where the expert GEMMs are compute-bound -----------------------------------
+    long_ms = None
+    if not args.no_long_prefill:
+        emb_long = (torch.randn(S_LONG, cfg.llm.hidden_size, device=dev) * 0.05).to(torch.bfloat16)
+        for _ in range(2):
+            llm.reset(); llm.prefill(emb_long.clone(), slot=0)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        tot = 0.0
+        for _ in range(3):
+            llm.reset()
+            x = emb_long.clone()
+            a.record(); llm.prefill(x, slot=0); b.record(); b.synchronize()
+            tot += a.elapsed_time(b)
+        long_ms = tot / 3
+        llm.reset()
+
     # ---- dominant kernel ------------------------------------------------------------------------------------
     c = cfg.llm
     if llm.mega is not None:
@@ -392,6 +411,10 @@ def run_b200(args):
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gu_bytes / 1e9 / (gu_ms / 1e3) / pk["hbm_gbs"],
                          "traffic": None, "bytes_per_launch": gu_bytes, "us_per_launch": gu_ms * 1e3,
                          "peak_source": pk["source"]},
+            "prefill_long": None if long_ms is None else {
+                "S": S_LONG, "ms": long_ms, "tflops": prefill_flops(S_LONG, cfg) / (long_ms / 1e3) / 1e12,
+                "tensor_frac": prefill_flops(S_LONG, cfg) / (long_ms / 1e3) / 1e12 / pk["tflops"],
+                "note": "Mixtral prefill only, 32 layers, one GPU, random embeddings (BASELINE configs[3] length)"},
             "e2e": {"value": world * NT / (e2e_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": images_h.numel() * 4 + feats_h.numel() * 4 + ids.numel() * 8,
                     "d2h_bytes_per_step": NT * 4, "ms_per_step": e2e_ms},
@@ -424,6 +447,7 @@ def main():
     ap.add_argument("--cpu-decode-tokens", type=int, default=4)
     ap.add_argument("--cpu-repeat", action="store_true", help="re-measure the CPU sample every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-long-prefill", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -83,7 +83,7 @@ int64_t vita_decode_attention_workspace_bytes(int64_t B, int64_t n_kv_heads, int
 int vita_decode_attention(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table,
                           const int32_t* cur_pos, void* out, void* workspace, int64_t B, int64_t n_q_heads,
                           int64_t n_kv_heads, int64_t head_dim, int64_t page_size, int64_t max_pages, int64_t splits,
-                          float scale, void* stream);
+                          float scale, int64_t q_stride /* elements between batch rows of q; 0 = dense */, void* stream);
 
 /* ---- sparse MoE (prefill) --------------------------------------------------------------------------------- */
 /* post_attention_layernorm + MixtralTopKRouter (modeling_mixtral.py:109-116; vLLM FusedMoE renormalize=True,
@@ -162,6 +162,12 @@ int vita_decode_moe_down(const void* act, const void* w2, const int32_t* topk_id
  * greedy step of HF generate(), video_audio_demo.py:257-270).  logits may be NULL; best[b] must be 0 on entry. */
 int vita_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
                         uint64_t* best, int64_t B, int64_t H, int64_t V, float eps, void* stream);
+
+/* batched decode through the GEMM path: per-sequence KV slots of the current positions, row-wise arg-max of bf16
+ * logits into the packed `best` words the decode chain consumes. */
+int vita_decode_slots(const int32_t* cur_pos, const int32_t* block_table, int32_t* slots, int64_t B, int64_t page_size,
+                      int64_t max_pages, void* stream);
+int vita_argmax_rows(const void* logits, uint64_t* best, int64_t B, int64_t V, void* stream);
 
 /* ---- greedy decode step on the tensor cores (tcgen05 swap-AB GEMV, stream-K) ---------------------------------
  * Same operations and epilogues as the vita_decode_* entry points above, with the weight tile as the M operand of

@@ -283,3 +283,27 @@ def test_single_kernel_decode_step_matches_per_kernel_path(geometry, monkeypatch
     while n < len(toks) and bool(clear[n]):
         n += 1
     assert gen_mega.sequences[0, n_prompt:n_prompt + n].tolist() == toks[:n]
+
+
+def test_batched_decode_matches_single_sequence_decode(tiny):
+    """BASELINE configs[4] shape (concurrent requests, paged KV, one token per request per step): the batched step
+    (GEMM path, M = B rows at B different positions) must reproduce each request's own greedy decode."""
+    from vita_b200.model.vita_mixtral import VITAMixtralForCausalLM
+    cfg, state, _ = tiny
+    model = VITAMixtralForCausalLM(cfg, W.pack(state, cfg, "cuda"), "cuda", max_batch=3, max_new_tokens=16,
+                                   shuffle_pages=True)
+    g = torch.Generator().manual_seed(21)
+    reqs = [{"input_ids": torch.randint(0, cfg.llm.vocab_size, (1, n), generator=g)} for n in (9, 17, 30)]
+    singles, rows = [], []
+    for r in reqs:
+        out = model.generate(r["input_ids"], max_new_tokens=6, output_scores=True, use_graph=False)
+        singles.append(out.sequences[0, r["input_ids"].shape[1]:].tolist())
+        rows.append(torch.cat([s.float().cpu() for s in out.scores]))
+    for use_graph in (False, True):
+        batch = model.generate_batch(reqs, max_new_tokens=6, use_graph=use_graph)
+        for b in range(3):
+            clear = _margin_ok(rows[b], 0.03 * rows[b].abs().max())
+            n = 0
+            while n < 6 and bool(clear[n]):
+                n += 1
+            assert batch[b][:n] == singles[b][:n], (b, use_graph, batch[b], singles[b], clear.tolist())

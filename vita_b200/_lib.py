@@ -28,7 +28,9 @@ SIGNATURES = {
     "vita_rope_kv_write": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "vita_attention_fwd": (c_int, [P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P, c_int, c_float, P]),
     "vita_decode_attention_workspace_bytes": (I64, [I64, I64, I64]),
-    "vita_decode_attention": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, P]),
+    "vita_decode_attention": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, I64, P]),
+    "vita_decode_slots": (c_int, [P, P, P, I64, I64, I64, P]),
+    "vita_argmax_rows": (c_int, [P, P, I64, I64, P]),
     "vita_moe_router": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_float, P]),
     "vita_moe_align": (c_int, [P, P, P, P, P, P, I64, I64, P]),
     "vita_moe_gemm_gate_up_silu": (c_int, [P, P, P, P, I64, I64, I64, I64, P]),

@@ -257,7 +257,8 @@ constexpr int DEC_D = 128;     // head dim
 constexpr int DEC_GROUP = 4;   // query heads per kv head (32 / 8)
 
 struct DecodeAttnParams {
-    const __nv_bfloat16* q;        // [B, n_q, D]
+    const __nv_bfloat16* q;        // row b at q + b * q_stride: [n_q, D]
+    long long q_stride;
     const __nv_bfloat16* k_cache;  // [slots, n_kv, D]
     const __nv_bfloat16* v_cache;
     const int* block_table;        // [B, max_pages]
@@ -292,7 +293,7 @@ decode_attn_kernel(const DecodeAttnParams p) {
     float q[DEC_GROUP][16];
 #pragma unroll
     for (int h = 0; h < DEC_GROUP; ++h) {
-        const uint4* qp = reinterpret_cast<const uint4*>(p.q + (static_cast<long long>(b) * p.n_q + kvh * DEC_GROUP + h) * DEC_D + d0);
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(b) * p.q_stride + (kvh * DEC_GROUP + h) * DEC_D + d0);
         const uint4 a = qp[0], c = qp[1];
         const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
@@ -465,12 +466,14 @@ extern "C" int64_t vita_decode_attention_workspace_bytes(int64_t B, int64_t n_kv
 extern "C" int vita_decode_attention(const void* q, const void* k_cache, const void* v_cache,
                                      const int32_t* block_table, const int32_t* cur_pos, void* out, void* workspace,
                                      int64_t B, int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim,
-                                     int64_t page_size, int64_t max_pages, int64_t splits, float scale, void* stream) {
+                                     int64_t page_size, int64_t max_pages, int64_t splits, float scale, int64_t q_stride,
+                                     void* stream) {
     VITA_REQUIRE(head_dim == DEC_D && n_q_heads == n_kv_heads * DEC_GROUP, "decode attention: need D=128, GQA group 4");
     VITA_REQUIRE(splits >= 1 && splits <= 16 && workspace != nullptr, "1 <= splits <= 16 and a workspace are required");
     if (B == 0) return VITA_OK;
     DecodeAttnParams p{};
-    p.q = BF16C(q); p.k_cache = BF16C(k_cache); p.v_cache = BF16C(v_cache);
+    p.q = BF16C(q); p.q_stride = q_stride > 0 ? q_stride : n_q_heads * head_dim;
+    p.k_cache = BF16C(k_cache); p.v_cache = BF16C(v_cache);
     p.block_table = block_table; p.cur_pos = cur_pos; p.out = static_cast<__nv_bfloat16*>(out);
     const int64_t n = B * n_kv_heads * splits * DEC_GROUP;
     // tickets first (must be zero-initialised once by the caller; the kernel resets them)

@@ -617,9 +617,57 @@ decode_router_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* _
     }
 }
 
+// Row-wise arg-max of bf16 logits (first index on ties, like torch.argmax), packed like the GEMV kernels do.
+__global__ void __launch_bounds__(256)
+argmax_rows_kernel(const __nv_bfloat16* __restrict__ logits, unsigned long long* __restrict__ best, int V) {
+    __shared__ unsigned long long red[8];
+    const __nv_bfloat16* row = logits + static_cast<long long>(blockIdx.x) * V;
+    unsigned long long loc = 0ull;
+    for (int i = threadIdx.x; i < V; i += 256) {
+        const unsigned long long k = pack_argmax(__bfloat162float(row[i]), i);
+        loc = k > loc ? k : loc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, loc, o);
+        loc = other > loc ? other : loc;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = red[0];
+        for (int i = 1; i < 8; ++i) m = red[i] > m ? red[i] : m;
+        best[blockIdx.x] = m;
+    }
+}
+
+// slots[b] = paged-KV slot of position cur_pos[b] of sequence b (batched decode through the GEMM path)
+__global__ void decode_slots_kernel(const int* __restrict__ cur_pos, const int* __restrict__ block_table,
+                                    int* __restrict__ slots, int B, int page_size, int max_pages) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int pos = cur_pos[b];
+    slots[b] = block_table[static_cast<long long>(b) * max_pages + pos / page_size] * page_size + pos % page_size;
+}
+
 }  // namespace vita
 
 using namespace vita;
+
+extern "C" int vita_argmax_rows(const void* logits, uint64_t* best, int64_t B, int64_t V, void* stream) {
+    if (B == 0) return VITA_OK;
+    argmax_rows_kernel<<<static_cast<unsigned>(B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        BF16C(logits), reinterpret_cast<unsigned long long*>(best), (int)V);
+    return check_launch("argmax_rows");
+}
+
+extern "C" int vita_decode_slots(const int32_t* cur_pos, const int32_t* block_table, int32_t* slots, int64_t B,
+                                 int64_t page_size, int64_t max_pages, void* stream) {
+    if (B == 0) return VITA_OK;
+    decode_slots_kernel<<<static_cast<unsigned>((B + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        cur_pos, block_table, slots, (int)B, (int)page_size, (int)max_pages);
+    return check_launch("decode_slots");
+}
 
 extern "C" int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* gen_count, int64_t max_log,
                                  int32_t* cache_len, int32_t* cur_pos, const void* embed, void* h, int64_t B,

@@ -87,6 +87,9 @@ class MixtralDecoder:
                                        cfg.vocab_size, decode_splits, dev)
         self._graph = None
         self._graph_batch = None
+        self._bgraph = None
+        self._bgraph_B = None
+        self.d_slots = torch.zeros(B, dtype=torch.int32, device=dev)
         self._prefill_ws = {}
         # expert parallelism: this rank holds experts [e_lo, e_hi) of every layer; attention, router, embeddings and
         # the KV cache are replicated, the partial MoE outputs are summed with one all-reduce per layer
@@ -102,6 +105,7 @@ class MixtralDecoder:
         if S > cap:
             c = self.cfg
             cap = max(S, 2 * cap, 128)
+            self._bgraph = None   # the batched-step graph references the old workspaces
             H, I, E, dev = c.hidden_size, c.intermediate_size, c.num_local_experts, self.device
             self._prefill_ws = dict(
                 cap=cap,
@@ -258,6 +262,69 @@ class MixtralDecoder:
             self._restore_state(self._snapshot)   # capture does not execute, but keep the invariant explicit
             self._graph, self._graph_batch = g, key
         self._graph.replay()
+
+    # ------------------------------------------------------------------------------------------ batched decode
+    def _batched_step_kernels(self, B: int, want_logits: bool):
+        """One token for each of B sequences through the GEMM path (weights of every touched expert are streamed once
+        for the whole batch; BASELINE configs[4]).  Same kernels as the prefill, with M = B rows at B different
+        positions, + the paged decode attention."""
+        c, w, cache = self.cfg, self.w, self.cache
+        nq, nkv, D, E, H = c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.num_local_experts, c.hidden_size
+        ws = self._ws(max(B, 16))
+        h = self.d_h[:B]
+        ops.decode_embed(self.best[:B], self.token_log[:B], self.gen_count[:B], cache.cache_len[:B], cache.cur_pos[:B],
+                         w["embed"], h)
+        slots = self.d_slots[:B]
+        ops.decode_slots(cache.cur_pos[:B], cache.block_table[:B], slots, cache.page_size)
+        xn, qkv, attn, xn2 = ws["xn"][:B], ws["qkv"][:B], ws["attn"][:B], ws["xn2"][:B]
+        ids, tw = ws["ids"][:B], ws["tw"][:B]
+        perm, rtok, rw = ws["perm"][:2 * B], ws["rtok"][:2 * B], ws["rw"][:2 * B]
+        xp, act, yp = ws["xp"][:2 * B], ws["act"][:2 * B], ws["yp"][:2 * B]
+        layers = w["layers"]
+        ops.rmsnorm(h, layers[0]["ln1"], c.rms_norm_eps, out=xn)
+        for li, lw in enumerate(layers):
+            ops.linear(xn, lw["wqkv"], out=qkv)
+            ops.rope_kv_write(qkv, cache.cur_pos[:B], slots, w["rope"], cache.k[li], cache.v[li], nq, nkv, D)
+            ops.decode_attention(qkv, cache.k[li], cache.v[li], cache.block_table[:B], cache.cur_pos[:B], attn,
+                                 self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits, D ** -0.5,
+                                 q_stride=c.qkv_rows)
+            ops.linear(attn, lw["wo"], residual=h, out=h)
+            ops.moe_router(h, lw["ln2"], lw["gate"], xn2, ids, tw, c.rms_norm_eps)
+            ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, B, E)
+            ops.row_copy(xn2, rtok, None, xp, 2 * B)
+            ops.moe_gate_up(xp, lw["w13"], act, ws["offs"], 2 * B)
+            ops.moe_down(act, lw["w2"], yp, ws["offs"], rw, 2 * B)
+            nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else w["norm"]
+            ops.moe_combine(h, yp, perm, nxt, xn, c.rms_norm_eps)
+        logits = ops.linear(xn, w["lm_head"], out=self.d_logits[:B])
+        ops.argmax_rows(logits, self.best[:B])
+
+    @property
+    def launches_per_batched_step(self) -> int:
+        return 5 + 11 * self.cfg.num_hidden_layers
+
+    @torch.no_grad()
+    def decode_step_batched(self, B: int, use_graph: bool = True):
+        assert self.ep_world == 1 and 1 <= B <= self.max_batch
+        if not use_graph:
+            self._batched_step_kernels(B, False)
+            return
+        if self._bgraph is None or self._bgraph_B != B:
+            snap = self._save_state()
+            self._batched_step_kernels(B, False)          # warm-up (cudaFuncSetAttribute etc.)
+            torch.cuda.synchronize()
+            self._restore_state(snap)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    self._batched_step_kernels(B, False)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._restore_state(snap)
+            self._bgraph, self._bgraph_B = g, B
+        self._bgraph.replay()
 
     def _save_state(self):
         c = self.cache

@@ -244,6 +244,26 @@ class VITAMixtralForCausalLM:
     __call__ = forward
 
     @torch.no_grad()
+    def generate_batch(self, requests, max_new_tokens: int = 16, use_graph: bool = True, step_callback=None):
+        """Concurrent greedy decode of several independent requests (BASELINE configs[4]: duplex / bs=16 streaming).
+
+        `requests`: list of dicts {"input_ids": [1, L], "images": ..., "audios": ...}.  Each request is prefilled
+        into its own paged-KV slot, then all of them advance one token per step through the batched decode step.
+        Returns the list of generated token lists.  `step_callback(step_index)` is called after every step launch
+        (latency harnesses record CUDA events there)."""
+        B = len(requests)
+        assert 1 <= B <= self.llm.max_batch and max_new_tokens <= self.llm.max_new_tokens
+        self.llm.reset()
+        for b, r in enumerate(requests):
+            emb, lens = self._embeds_for(r["input_ids"], r.get("images"), r.get("audios"))
+            self.llm.prefill(emb[0, : lens[0]].contiguous(), slot=b)
+        for step in range(max_new_tokens):
+            self.llm.decode_step_batched(B, use_graph=use_graph)
+            if step_callback is not None:
+                step_callback(step)
+        return [self.llm.generated_tokens(b)[:max_new_tokens] for b in range(B)]
+
+    @torch.no_grad()
     def generate(self, input_ids, images=None, audios=None, do_sample=False, temperature=None, top_p=None,
                  num_beams=1, output_scores=False, return_dict_in_generate=True, max_new_tokens=16, use_cache=True,
                  stopping_criteria=None, eos_token_id: Optional[int] = None, use_graph: bool = True, sync_every: int = 16,

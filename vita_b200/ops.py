@@ -124,13 +124,25 @@ def decode_attention_workspace(B: int, n_kv: int, splits: int, device) -> torch.
 
 
 def decode_attention(q, k_cache, v_cache, block_table, cur_pos, out, workspace, n_q, n_kv, head_dim, page_size,
-                     splits, scale) -> torch.Tensor:
-    _chk(q, BF16, "q"); _chk(k_cache, BF16, "k_cache"); _chk(v_cache, BF16, "v_cache"); _chk(out, BF16, "out")
+                     splits, scale, q_stride: int = 0) -> torch.Tensor:
+    _chk(q, BF16, "q", contiguous=False); _chk(k_cache, BF16, "k_cache"); _chk(v_cache, BF16, "v_cache")
+    _chk(out, BF16, "out")
     _chk(block_table, torch.int32, "block_table"); _chk(cur_pos, torch.int32, "cur_pos")
     B = cur_pos.shape[0]
     _lib.call("vita_decode_attention", _p(q), _p(k_cache), _p(v_cache), _p(block_table), _p(cur_pos), _p(out),
-              _p(workspace), B, n_q, n_kv, head_dim, page_size, block_table.shape[1], splits, float(scale), _stream())
+              _p(workspace), B, n_q, n_kv, head_dim, page_size, block_table.shape[1], splits, float(scale), q_stride,
+              _stream())
     return out
+
+
+def decode_slots(cur_pos, block_table, slots, page_size):
+    _lib.call("vita_decode_slots", _p(cur_pos), _p(block_table), _p(slots), cur_pos.shape[0], page_size,
+              block_table.shape[1], _stream())
+
+
+def argmax_rows(logits, best):
+    _chk(logits, BF16, "logits"); _chk(best, torch.int64, "best")
+    _lib.call("vita_argmax_rows", _p(logits), _p(best), logits.shape[0], logits.shape[1], _stream())
 
 
 # ------------------------------------------------------------------------------------------------ MoE (prefill)
