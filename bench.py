@@ -183,16 +183,20 @@ def pick_cpu_threads() -> int:
     prefill-shaped product at a few thread counts and keep the fastest."""
     n = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, n) if c <= n})
-    w = torch.randn(8192, 4096)
-    x1, xs = torch.randn(1, 4096), torch.randn(256, 4096)
+    # a slice of the real workload: one InternViT-layer-sized block (1025 tokens) and one expert mat-vec
+    w_qkv, w_e = torch.randn(3072, 1024), torch.randn(8192, 4096)
+    xs, x1 = torch.randn(1, 1025, 1024), torch.randn(1, 4096)
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
         for _ in range(2):
             t0 = time.perf_counter()
-            for _ in range(4):
-                (x1 @ w.T).sum().item()
-            (xs @ w.T).sum().item()
+            y = torch.nn.functional.layer_norm(xs, (1024,))
+            qkv = (y @ w_qkv.T).view(1, 1025, 3, 16, 64).permute(2, 0, 3, 1, 4)
+            a = ((qkv[0] * 0.125) @ qkv[1].transpose(-1, -2)).softmax(-1) @ qkv[2]
+            a.sum().item()
+            for _ in range(8):
+                (x1 @ w_e.T).sum().item()
             dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = c, dt
@@ -358,27 +362,35 @@ def run_b200(args):
         # per-kernel path: the expert gate/up GEMV (60% of the decode bytes), timed with CUDA events on the launching
         # stream in an eager pass right after the timed region (inside it the step is one CUDA graph)
         lw = packed["llm"]["layers"]
-        reps, gu_ms = 3, 0.0
-        for r in range(reps + 1):
+
+        def launch_all():
             for li in range(len(lw)):
-                a, b = ev(), ev()
-                a.record()
                 if llm.use_tc:
                     ops.decode_tc_moe_gate_up(llm.d_h[:1], lw[li]["ln2"], lw[li]["gate"], lw[li]["w13"], llm.d_ids[:1],
                                               llm.d_w[:1], llm.d_act[:1], llm.tc_ws, c.rms_norm_eps)
                 else:
                     ops.decode_moe_gate_up(llm.d_h[:1], lw[li]["ln2"], lw[li]["gate"], lw[li]["w13"], llm.d_ids[:1],
                                            llm.d_w[:1], llm.d_act[:1], c.rms_norm_eps)
-                b.record()
-                b.synchronize()
-                if r > 0:
-                    gu_ms += a.elapsed_time(b)
+
+        # one launch per layer (32 different 470 MB weight sets, far larger than L2), back to back on the stream;
+        # average duration = elapsed / launches
+        launch_all()
+        torch.cuda.synchronize()
+        reps, gu_ms = 3, 0.0
+        for r in range(reps):
+            a, b = ev(), ev()
+            a.record()
+            launch_all()
+            b.record()
+            b.synchronize()
+            gu_ms += a.elapsed_time(b)
         gu_ms /= reps * len(lw)
         gu_bytes = c.num_experts_per_tok * 2 * c.intermediate_size * c.hidden_size * 2 + c.hidden_size * 2 \
             + c.num_experts_per_tok * c.intermediate_size * 2 + c.num_local_experts * c.hidden_size * 2
         roof_kernel = ("tc_gemv_kernel<TcGateUpOp>" if llm.use_tc else "stream_gemv_kernel<GateUpOp>") + \
             " (decode: fused RMSNorm + router + the 2 selected experts' gate/up rows + SiLU*up)"
-        roof_note = "eager launches timed with CUDA events right after the timed region"
+        roof_note = ("one launch per layer back to back on the stream, CUDA events around the batch, right after the timed "
+                     "region (inside it the decode step is a single CUDA graph)")
     pk = peaks()
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------------------
