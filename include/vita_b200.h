@@ -93,7 +93,8 @@ int vita_moe_router(const void* h, const void* norm_w, const void* gate_w, void*
 /* stable counting sort of the (token, k) assignments by expert: expert_offsets [E+1], perm_row [n_tok*2],
  * row_token [n_tok*2], row_weight [n_tok*2] (replaces the one_hot / torch.where bookkeeping, modeling_mixtral.py:81-90). */
 int vita_moe_align(const int32_t* topk_ids, const float* topk_w, int32_t* expert_offsets, int32_t* perm_row,
-                   int32_t* row_token, float* row_weight, int64_t n_tok, int64_t E, void* stream);
+                   int32_t* row_token, float* row_weight, int32_t* row_assign /* [n_tok*2] t*2+k per row, may be NULL */,
+                   int64_t n_tok, int64_t E, void* stream);
 /* grouped expert GEMMs over the permuted rows (modeling_mixtral.py:91-95):
  *   Act[r, :]    = silu(X[r] . Wg_e^T) * (X[r] . Wu_e^T)   with W_gate_up [E, 2I, H] (gate rows first)
  *   Y_perm[r, :] = row_weight[r] * (Act[r] . Wd_e^T)       with W_down [E, H, I] */
@@ -106,7 +107,22 @@ int vita_moe_gemm_down(const void* Act, const void* W_down, void* Y_perm, const 
 int vita_moe_combine(void* h, const void* y_perm, const int32_t* perm_row, const void* next_norm_w, void* xn_out,
                      int64_t n_tok, int64_t H, float eps, void* stream);
 
-/* expert-parallel tail of a decoder layer: h += y where y is the all-reduced sum of the ranks' partial MoE outputs
+/* ---- expert-parallel MoE over NVLink peer memory (fused compute + collective) -----------------------------
+ * vita_moe_gemm_down_ep: the down-projection GEMM whose epilogue stores each (token, k) output row directly into the
+ * receive buffer of the rank that owns the token (peer_out[rank] -> [chunk, 2, H] bf16 in symmetric memory).
+ * vita_ep_signal / vita_ep_wait: epoch flags in symmetric memory (flags [2][n_ranks] per rank; which = 0 "rows
+ * landed", 1 "h/xn gathered").  vita_ep_reduce_norm_gather: the owner sums its two slots per token into the residual
+ * stream, applies the next RMSNorm and writes both rows into every rank's h / xn (all-gather by P2P stores). */
+int vita_moe_gemm_down_ep(const void* Act, const void* W_down, const int32_t* expert_offsets, const float* row_weight,
+                          const int32_t* row_assign, void* const* peer_out, int64_t rows, int64_t num_local_experts,
+                          int64_t H, int64_t I, int64_t chunk, void* stream);
+int vita_ep_signal(void* const* peer_flags, int64_t which, int64_t n_ranks, int64_t my_rank, int64_t epoch, void* stream);
+int vita_ep_wait(const int32_t* my_flags, int64_t which, int64_t n_ranks, int64_t epoch, void* stream);
+int vita_ep_reduce_norm_gather(const void* rs_buf, const int32_t* my_flags, void* const* peer_h, void* const* peer_xn,
+                               const void* next_norm_w, int64_t tok0, int64_t n_owned, int64_t n_ranks, int64_t my_rank,
+                               int64_t epoch, int64_t H, float eps, void* stream);
+
+/* expert-parallel tail of a decoder layer (NCCL variant): h += y where y is the all-reduced sum of the ranks' partial MoE outputs
  * (each rank ran vita_moe_combine on a zeroed buffer with only its local experts' rows filled); optional next RMSNorm. */
 int vita_add_rmsnorm(void* h, const void* y, const void* next_norm_w, void* xn_out, int64_t n_tok, int64_t H, float eps,
                      void* stream);

@@ -32,7 +32,11 @@ SIGNATURES = {
     "vita_decode_slots": (c_int, [P, P, P, I64, I64, I64, P]),
     "vita_argmax_rows": (c_int, [P, P, I64, I64, P]),
     "vita_moe_router": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_float, P]),
-    "vita_moe_align": (c_int, [P, P, P, P, P, P, I64, I64, P]),
+    "vita_moe_align": (c_int, [P, P, P, P, P, P, P, I64, I64, P]),
+    "vita_moe_gemm_down_ep": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, I64, P]),
+    "vita_ep_signal": (c_int, [P, I64, I64, I64, I64, P]),
+    "vita_ep_wait": (c_int, [P, I64, I64, I64, P]),
+    "vita_ep_reduce_norm_gather": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, I64, c_float, P]),
     "vita_moe_gemm_gate_up_silu": (c_int, [P, P, P, P, I64, I64, I64, I64, P]),
     "vita_moe_gemm_down": (c_int, [P, P, P, P, P, I64, I64, I64, I64, P]),
     "vita_moe_combine": (c_int, [P, P, P, P, P, I64, I64, c_float, P]),

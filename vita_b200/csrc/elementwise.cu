@@ -272,8 +272,8 @@ rmsnorm_router_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* 
 //   row_weight[n*2]     : routing weight of each permuted row (fp32)
 __global__ void __launch_bounds__(1024)
 moe_align_kernel(const int* __restrict__ topk_ids, const float* __restrict__ topk_w, int* __restrict__ expert_offsets,
-                 int* __restrict__ perm_row, int* __restrict__ row_token, float* __restrict__ row_weight, int n_assign,
-                 int E) {
+                 int* __restrict__ perm_row, int* __restrict__ row_token, float* __restrict__ row_weight,
+                 int* __restrict__ row_assign, int n_assign, int E) {
     __shared__ int counts[32];
     __shared__ int offs[33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -302,6 +302,7 @@ moe_align_kernel(const int* __restrict__ topk_ids, const float* __restrict__ top
                 perm_row[i] = r;
                 row_token[r] = i >> 1;
                 row_weight[r] = topk_w[i];
+                if (row_assign) row_assign[r] = i;
             }
             base += __popc(m);
         }
@@ -404,6 +405,94 @@ add_rmsnorm_kernel(__nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restric
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = f[j] * inv * g[j];
             xr[idx] = pack8(f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ expert-parallel tail
+// Flags live in symmetric memory: flags[which][src_rank] of every rank is written by src_rank with a monotonically
+// increasing epoch (st.release.sys after a system fence), waited for with ld.acquire.sys.
+__device__ __forceinline__ void sys_wait_flag(const int* flag, int epoch) {
+    int v;
+    long long t0 = clock64();
+    do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v < epoch && clock64() - t0 > VITA_MBAR_TIMEOUT_CYCLES * 4) {
+            printf("[vita] EP flag timeout: block %d waits for epoch %d, sees %d\n", blockIdx.x, epoch, v);
+            __trap();
+        }
+    } while (v < epoch);
+}
+
+__global__ void ep_signal_kernel(int* const* __restrict__ peer_flags, int which, int n_ranks, int my_rank, int epoch) {
+    __threadfence_system();
+    if (threadIdx.x < n_ranks) {
+        int* f = peer_flags[threadIdx.x] + which * n_ranks + my_rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+}
+
+__global__ void ep_wait_kernel(const int* __restrict__ my_flags, int which, int n_ranks, int epoch) {
+    if (threadIdx.x < n_ranks) sys_wait_flag(my_flags + which * n_ranks + threadIdx.x, epoch);
+}
+
+// Owner side of the expert-parallel combine: for each owned token t (one block each)
+//   h[t] += slot0[t] + slot1[t]      (the two expert outputs, pushed by the ranks holding those experts)
+//   xn[t] = RMSNorm(h[t]) * w        (optional)
+// and both rows are written into every rank's h / xn (all-gather by P2P stores).
+template <int THREADS, int VPT>
+__global__ void __launch_bounds__(THREADS)
+ep_reduce_norm_gather_kernel(const __nv_bfloat16* __restrict__ rs_buf, const int* __restrict__ my_flags,
+                             __nv_bfloat16* const* __restrict__ peer_h, __nv_bfloat16* const* __restrict__ peer_xn,
+                             const __nv_bfloat16* __restrict__ next_norm_w, int tok0, int n_ranks, int my_rank, int epoch,
+                             int H, float eps) {
+    __shared__ float red[32];
+    if (threadIdx.x < n_ranks) sys_wait_flag(my_flags + threadIdx.x, epoch);   // flags[0][src]: partial rows landed
+    __syncthreads();
+    const int lt = blockIdx.x;                    // local token index inside my chunk
+    const long long tok = tok0 + lt;
+    const int nvec = H >> 3;
+    const uint4* hr = reinterpret_cast<const uint4*>(peer_h[my_rank] + tok * H);
+    const uint4* s0 = reinterpret_cast<const uint4*>(rs_buf + (static_cast<long long>(lt) * 2) * H);
+    const uint4* s1 = reinterpret_cast<const uint4*>(rs_buf + (static_cast<long long>(lt) * 2 + 1) * H);
+    uint4 v[VPT];
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int idx = threadIdx.x + i * THREADS;
+        if (idx < nvec) {
+            float a[8], b[8], c[8];
+            unpack8(hr[idx], a);
+            unpack8(__ldcv(s0 + idx), b);
+            unpack8(__ldcv(s1 + idx), c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = a[j] + (b[j] + c[j]);
+            v[i] = pack8(a);
+            unpack8(v[i], a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss += a[j] * a[j];
+        }
+    }
+    const float tot = block_sum<THREADS>(ss, red);
+    const float inv = rsqrtf(tot / static_cast<float>(H) + eps);
+    const uint4* wr = reinterpret_cast<const uint4*>(next_norm_w);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int idx = threadIdx.x + i * THREADS;
+        if (idx < nvec) {
+            uint4 xo = make_uint4(0, 0, 0, 0);
+            if (next_norm_w) {
+                float f[8], g[8];
+                unpack8(v[i], f);
+                unpack8(__ldg(wr + idx), g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = f[j] * inv * g[j];
+                xo = pack8(f);
+            }
+            for (int r = 0; r < n_ranks; ++r) {
+                reinterpret_cast<uint4*>(peer_h[r] + tok * H)[idx] = v[i];
+                if (next_norm_w) reinterpret_cast<uint4*>(peer_xn[r] + tok * H)[idx] = xo;
+            }
         }
     }
 }
@@ -639,11 +728,12 @@ extern "C" int vita_moe_router(const void* h, const void* norm_w, const void* ga
 }
 
 extern "C" int vita_moe_align(const int32_t* topk_ids, const float* topk_w, int32_t* expert_offsets,
-                              int32_t* perm_row, int32_t* row_token, float* row_weight, int64_t n_tok, int64_t E,
-                              void* stream) {
+                              int32_t* perm_row, int32_t* row_token, float* row_weight, int32_t* row_assign,
+                              int64_t n_tok, int64_t E, void* stream) {
     VITA_REQUIRE(E >= 1 && E <= 32, "E must be in [1, 32]");
     moe_align_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(topk_ids, topk_w, expert_offsets, perm_row,
-                                                                        row_token, row_weight, (int)(n_tok * 2), (int)E);
+                                                                        row_token, row_weight, row_assign,
+                                                                        (int)(n_tok * 2), (int)E);
     return check_launch("moe_align");
 }
 
@@ -654,6 +744,34 @@ extern "C" int vita_moe_combine(void* h, const void* y_perm, const int32_t* perm
     moe_combine_kernel<256, 2><<<static_cast<unsigned>(n_tok), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         BFM(h), BF(y_perm), perm_row, BF(next_norm_w), BFM(xn_out), (int)H, eps);
     return check_launch("moe_combine");
+}
+
+extern "C" int vita_ep_signal(void* const* peer_flags, int64_t which, int64_t n_ranks, int64_t my_rank, int64_t epoch,
+                              void* stream) {
+    VITA_REQUIRE(n_ranks >= 1 && n_ranks <= 32, "n_ranks must be in [1, 32]");
+    ep_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<int* const*>(peer_flags), (int)which,
+                                                                      (int)n_ranks, (int)my_rank, (int)epoch);
+    return check_launch("ep_signal");
+}
+
+extern "C" int vita_ep_wait(const int32_t* my_flags, int64_t which, int64_t n_ranks, int64_t epoch, void* stream) {
+    VITA_REQUIRE(n_ranks >= 1 && n_ranks <= 32, "n_ranks must be in [1, 32]");
+    ep_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(my_flags, (int)which, (int)n_ranks, (int)epoch);
+    return check_launch("ep_wait");
+}
+
+extern "C" int vita_ep_reduce_norm_gather(const void* rs_buf, const int32_t* my_flags, void* const* peer_h,
+                                          void* const* peer_xn, const void* next_norm_w, int64_t tok0, int64_t n_owned,
+                                          int64_t n_ranks, int64_t my_rank, int64_t epoch, int64_t H, float eps,
+                                          void* stream) {
+    VITA_REQUIRE(H % 8 == 0 && H <= 8 * 2 * 256, "H must be a multiple of 8 and <= 4096");
+    VITA_REQUIRE(n_ranks >= 1 && n_ranks <= 32, "n_ranks must be in [1, 32]");
+    if (n_owned == 0) return VITA_OK;
+    ep_reduce_norm_gather_kernel<256, 2><<<static_cast<unsigned>(n_owned), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        BF(rs_buf), my_flags, reinterpret_cast<__nv_bfloat16* const*>(peer_h),
+        reinterpret_cast<__nv_bfloat16* const*>(peer_xn), BF(next_norm_w), (int)tok0, (int)n_ranks, (int)my_rank,
+        (int)epoch, (int)H, eps);
+    return check_launch("ep_reduce_norm_gather");
 }
 
 extern "C" int vita_add_rmsnorm(void* h, const void* y, const void* next_norm_w, void* xn_out, int64_t n_tok, int64_t H,

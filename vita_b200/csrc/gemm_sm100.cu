@@ -35,6 +35,11 @@ struct GemmArgs {
     const __nv_bfloat16* residual;  // [M, ldr] or nullptr
     long long ldr;
     int act;                    // VITA_ACT_*
+    // expert-parallel scatter epilogue (down projection): output row r goes to the rank that owns its token,
+    //   dst = peer_out[t / chunk] + ((t % chunk) * 2 + k) * ldc   with (t, k) = (row_assign[r] >> 1, row_assign[r] & 1)
+    const int* row_assign;
+    __nv_bfloat16* const* peer_out;
+    int chunk;
 };
 
 struct Tile {
@@ -181,6 +186,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float rs = (args.rowscale && valid) ? args.rowscale[grow] : 1.0f;
             const __nv_bfloat16* bias = args.bias ? args.bias + static_cast<long long>(t.group) * args.N : nullptr;
             __nv_bfloat16* crow = args.C + static_cast<long long>(grow) * args.ldc;
+            if (args.peer_out != nullptr && valid) {
+                const int a = args.row_assign[grow], tk = a >> 1;
+                const int owner = tk / args.chunk;
+                crow = args.peer_out[owner] + (static_cast<long long>(tk - owner * args.chunk) * 2 + (a & 1)) * args.ldc;
+            }
             const __nv_bfloat16* rrow = args.residual ? args.residual + static_cast<long long>(grow) * args.ldr : nullptr;
 #pragma unroll 1
             for (int c = 0; c < BN_OUT / 32; ++c) {
@@ -427,6 +437,30 @@ extern "C" int vita_moe_gemm_gate_up_silu(const void* X_perm, const void* W_gate
     VITA_REQUIRE(I % 8 == 0, "I must be a multiple of 8");
     return gemm_dispatch(X_perm, H, a.M, W_gate_up, static_cast<int>(2 * I), a, true,
                          static_cast<cudaStream_t>(stream));
+}
+
+// Expert-parallel down projection: the GEMM epilogue stores every output row straight into the symmetric-memory
+// receive buffer of the rank that owns the token (P2P stores over NVLink), so compute and the "combine" transfer are
+// one kernel; the owner later sums its two slots per token (vita_ep_reduce_norm_gather).
+extern "C" int vita_moe_gemm_down_ep(const void* Act, const void* W_down, const int32_t* expert_offsets,
+                                     const float* row_weight, const int32_t* row_assign, void* const* peer_out,
+                                     int64_t rows, int64_t num_local_experts, int64_t H, int64_t I, int64_t chunk,
+                                     void* stream) {
+    GemmArgs a{};
+    a.M = static_cast<int>(rows);
+    a.N = static_cast<int>(H);
+    a.K = static_cast<int>(I);
+    a.num_groups = static_cast<int>(num_local_experts);
+    a.group_offsets = expert_offsets;
+    a.C = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(Act));   // unused when peer_out is set; keeps checks happy
+    a.ldc = H;
+    a.rowscale = row_weight;
+    a.act = VITA_ACT_NONE;
+    a.row_assign = row_assign;
+    a.peer_out = reinterpret_cast<__nv_bfloat16* const*>(peer_out);
+    a.chunk = static_cast<int>(chunk);
+    VITA_REQUIRE(expert_offsets && row_assign && peer_out && chunk > 0, "offsets, row_assign, peer_out and chunk required");
+    return gemm_dispatch(Act, I, a.M, W_down, static_cast<int>(H), a, false, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vita_moe_gemm_down(const void* Act, const void* W_down, void* Y_perm, const int32_t* expert_offsets,

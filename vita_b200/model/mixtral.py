@@ -97,6 +97,37 @@ class MixtralDecoder:
         per = cfg.num_local_experts // self.ep_world
         self.e_lo, self.e_hi = self.ep_rank * per, (self.ep_rank + 1) * per
         assert weights["layers"][0]["w13"].shape[0] == per, "expert tensors do not match the EP layout"
+        self.ep_p2p = None
+        if self.ep_world > 1 and os.environ.get("VITA_B200_EP", "p2p") == "p2p":
+            self._init_ep_p2p()
+
+    def _init_ep_p2p(self):
+        """Symmetric (peer-mapped) buffers for the fused expert-parallel combine: every rank can store into every
+        other rank's receive slots, residual stream and normed activations over NVLink."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        c, N, dev = self.cfg, self.ep_world, self.device
+        H, S_max = c.hidden_size, self.cache.max_seq_len
+        chunk_max = (S_max + N - 1) // N
+        al = lambda n: (n + 255) // 256 * 256
+        sizes = [al(chunk_max * 2 * H * 2), al(S_max * H * 2), al(S_max * H * 2), al(2 * N * 4)]
+        offs = [0]
+        for z in sizes:
+            offs.append(offs[-1] + z)
+        sym = symm_mem.empty(offs[-1], dtype=torch.uint8, device=dev)
+        sym.zero_()
+        torch.cuda.synchronize()
+        hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
+        delta = sym.data_ptr() - int(hdl.buffer_ptrs[hdl.rank])      # offset of this tensor inside the allocation
+        bases = [int(p) + delta for p in hdl.buffer_ptrs]
+        assert hdl.world_size == N and hdl.rank == self.ep_rank
+        view = lambda i, dt: sym[offs[i]:offs[i] + sizes[i]].view(dt)
+        ptrs = lambda i: torch.tensor([b + offs[i] for b in bases], dtype=torch.int64, device=dev)
+        self.ep_p2p = dict(
+            sym=sym, hdl=hdl, chunk_max=chunk_max,
+            rs=view(0, BF16), h=view(1, BF16).view(S_max, H), xn=view(2, BF16).view(S_max, H),
+            flags=view(3, torch.int32), rs_ptrs=ptrs(0), h_ptrs=ptrs(1), xn_ptrs=ptrs(2), flag_ptrs=ptrs(3), epoch=0)
+        dist.barrier()
 
     # ------------------------------------------------------------------------------------------ prefill
     def _ws(self, S: int):
@@ -123,6 +154,7 @@ class MixtralDecoder:
                 act=torch.empty(cap * 2, I, dtype=BF16, device=dev),
                 yp=torch.empty(cap * 2, H, dtype=BF16, device=dev),
                 ybuf=torch.empty(cap, H, dtype=BF16, device=dev) if self.ep_world > 1 else None,
+                rassign=torch.empty(cap * 2, dtype=torch.int32, device=dev),
                 pos=torch.arange(cap, dtype=torch.int32, device=dev))
         return self._prefill_ws
 
@@ -139,8 +171,14 @@ class MixtralDecoder:
         assert S <= self.cache.max_seq_len
         ws = self._ws(S)
         h = inputs_embeds
+        p2p = self.ep_p2p
+        if p2p is not None:          # the residual stream and the normed activations live in symmetric memory
+            h = p2p["h"][:S]
+            h.copy_(inputs_embeds)
         nq, nkv, D, E = c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.num_local_experts
         xn, qkv, attn, xn2 = ws["xn"][:S], ws["qkv"][:S], ws["attn"][:S], ws["xn2"][:S]
+        if p2p is not None:
+            xn = p2p["xn"][:S]
         ids, tw = ws["ids"][:S], ws["tw"][:S]
         perm, rtok, rw = ws["perm"][:2 * S], ws["rtok"][:2 * S], ws["rw"][:2 * S]
         xp, act, yp = ws["xp"][:2 * S], ws["act"][:2 * S], ws["yp"][:2 * S]
@@ -156,10 +194,26 @@ class MixtralDecoder:
                           (0, nq * D, D), 1, nq, nkv, S, S, D, D, None, True, D ** -0.5)
             ops.linear(attn, lw["wo"], residual=h, out=h)
             ops.moe_router(h, lw["ln2"], lw["gate"], xn2, ids, tw, c.rms_norm_eps)
-            ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, S, E)
+            ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, S, E, row_assign=ws["rassign"][:2 * S])
             ops.row_copy(xn2, rtok, None, xp, 2 * S)
             nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else (w["norm"] if all_logits else None)
-            if self.ep_world == 1:
+            if p2p is not None:
+                # fused expert-parallel combine over NVLink peer memory: the down-projection epilogue pushes every
+                # (token, k) row to the token's owner; owners reduce + norm + all-gather by P2P stores
+                N, r = self.ep_world, self.ep_rank
+                chunk = (S + N - 1) // N
+                offs_local = ws["offs"][self.e_lo:]
+                p2p["epoch"] += 1
+                ep = p2p["epoch"]
+                ops.moe_gate_up(xp, lw["w13"], act, offs_local, 2 * S)
+                ops.moe_down_ep(act, lw["w2"], offs_local, rw, ws["rassign"][:2 * S], p2p["rs_ptrs"], 2 * S, chunk)
+                ops.ep_signal(p2p["flag_ptrs"], 0, N, r, ep)
+                n_owned = max(0, min(chunk, S - r * chunk))
+                ops.ep_reduce_norm_gather(p2p["rs"], p2p["flags"], p2p["h_ptrs"], p2p["xn_ptrs"], nxt, r * chunk,
+                                          n_owned, N, r, ep, H, c.rms_norm_eps)
+                ops.ep_signal(p2p["flag_ptrs"], 1, N, r, ep)
+                ops.ep_wait(p2p["flags"], 1, N, ep)
+            elif self.ep_world == 1:
                 ops.moe_gate_up(xp, lw["w13"], act, ws["offs"], 2 * S)
                 ops.moe_down(act, lw["w2"], yp, ws["offs"], rw, 2 * S)
                 ops.moe_combine(h, yp, perm, nxt, xn if nxt is not None else None, c.rms_norm_eps)

@@ -154,13 +154,35 @@ def moe_router(h, norm_w, gate_w, xn, topk_ids, topk_w, eps):
               gate_w.shape[0], float(eps), _stream())
 
 
-def moe_align(topk_ids, topk_w, expert_offsets, perm_row, row_token, row_weight, n_tok, E):
+def moe_align(topk_ids, topk_w, expert_offsets, perm_row, row_token, row_weight, n_tok, E, row_assign=None):
     for t, n in ((topk_ids, "topk_ids"), (expert_offsets, "expert_offsets"), (perm_row, "perm_row"),
                  (row_token, "row_token")):
         _chk(t, torch.int32, n)
     _chk(topk_w, torch.float32, "topk_w"); _chk(row_weight, torch.float32, "row_weight")
     _lib.call("vita_moe_align", _p(topk_ids), _p(topk_w), _p(expert_offsets), _p(perm_row), _p(row_token),
-              _p(row_weight), n_tok, E, _stream())
+              _p(row_weight), _p(row_assign), n_tok, E, _stream())
+
+
+def moe_down_ep(act, w_down, expert_offsets, row_weight, row_assign, peer_out_ptrs, rows, chunk):
+    """Down projection of the local experts; the epilogue pushes each row to its token's owner over NVLink."""
+    _chk(act, BF16, "act"); _chk(w_down, BF16, "w_down"); _chk(peer_out_ptrs, torch.int64, "peer_out_ptrs")
+    E, H, I = w_down.shape
+    _lib.call("vita_moe_gemm_down_ep", _p(act), _p(w_down), _p(expert_offsets), _p(row_weight), _p(row_assign),
+              _p(peer_out_ptrs), rows, E, H, I, chunk, _stream())
+
+
+def ep_signal(peer_flag_ptrs, which, n_ranks, my_rank, epoch):
+    _lib.call("vita_ep_signal", _p(peer_flag_ptrs), which, n_ranks, my_rank, epoch, _stream())
+
+
+def ep_wait(my_flags, which, n_ranks, epoch):
+    _lib.call("vita_ep_wait", _p(my_flags), which, n_ranks, epoch, _stream())
+
+
+def ep_reduce_norm_gather(rs_buf, my_flags, peer_h_ptrs, peer_xn_ptrs, next_norm_w, tok0, n_owned, n_ranks, my_rank,
+                          epoch, H, eps):
+    _lib.call("vita_ep_reduce_norm_gather", _p(rs_buf), _p(my_flags), _p(peer_h_ptrs), _p(peer_xn_ptrs),
+              _p(next_norm_w), tok0, n_owned, n_ranks, my_rank, epoch, H, float(eps), _stream())
 
 
 def moe_gate_up(x_perm, w_gate_up, act, expert_offsets, rows):
