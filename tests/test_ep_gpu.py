@@ -1,4 +1,7 @@
-"""Expert-parallel prefill (NCCL all-reduce of the partial MoE outputs) vs the single-GPU model; needs >= 2 GPUs."""
+"""Expert-parallel prefill vs the single-GPU model with identical weights; needs >= 2 GPUs (gpurun --gpus 2).
+  p2p : the down-projection GEMM epilogue pushes rows to the token owners over NVLink peer memory (fused)
+  nccl: partial sums + one NCCL all-reduce per layer (baseline)"""
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -10,11 +13,12 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 @pytest.mark.gpu
-def test_ep2_prefill_matches_single_gpu():
+@pytest.mark.parametrize("mode,port", [("p2p", 29533), ("nccl", 29534)])
+def test_ep2_prefill_matches_single_gpu(mode, port):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", str(ROOT / "tests" / "ep_check.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+           "127.0.0.1", "--master-port", str(port), str(ROOT / "tests" / "ep_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, VITA_B200_EP=mode))
     print(res.stdout[-2000:], res.stderr[-2000:])
     assert res.returncode == 0
