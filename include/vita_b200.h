@@ -184,6 +184,8 @@ int vita_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, con
 int vita_decode_slots(const int32_t* cur_pos, const int32_t* block_table, int32_t* slots, int64_t B, int64_t page_size,
                       int64_t max_pages, void* stream);
 int vita_argmax_rows(const void* logits, uint64_t* best, int64_t B, int64_t V, void* stream);
+/* hint: pull `bytes` at `ptr` into L2 (cp.async.bulk.prefetch.L2), e.g. the o-projection weights during attention */
+int vita_l2_prefetch(const void* ptr, int64_t bytes, void* stream);
 
 /* ---- greedy decode step on the tensor cores (tcgen05 swap-AB GEMV, stream-K) ---------------------------------
  * Same operations and epilogues as the vita_decode_* entry points above, with the weight tile as the M operand of

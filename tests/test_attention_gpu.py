@@ -38,6 +38,23 @@ def test_mixtral_causal_gqa(S):
     assert_close(out, ref, rel=2e-2, what=f"causal gqa S={S}")
 
 
+def test_mixtral_causal_gqa_long_128_row_ctas():
+    """Long prefill shape: enough CTAs that the 128-query-row variant of the kernel is selected."""
+    from vita_b200 import ops
+    nq, nkv, D, S = 32, 8, 128, 1300
+    qkv = randn((S, (nq + 2 * nkv) * D), 5)
+    qd = to_dev(qkv)
+    out = torch.empty(S, nq * D, dtype=BF16, device="cuda")
+    W = (nq + 2 * nkv) * D
+    ops.attention(qd, qd[:, nq * D:], qd[:, (nq + nkv) * D:], out, (0, W, D), (0, W, D), (0, W, D), (0, nq * D, D),
+                  1, nq, nkv, S, S, D, D, None, True, D ** -0.5)
+    q = qkv[:, : nq * D].view(S, nq, D).transpose(0, 1)[None]
+    k = qkv[:, nq * D: (nq + nkv) * D].view(S, nkv, D).transpose(0, 1)[None]
+    v = qkv[:, (nq + nkv) * D:].view(S, nkv, D).transpose(0, 1)[None]
+    ref = _ref_attn(q, k, v, D ** -0.5, True)[0].transpose(0, 1).reshape(S, nq * D)
+    assert_close(out, ref, rel=2e-2, what="causal gqa, 128-row CTAs")
+
+
 @pytest.mark.parametrize("N,S", [(2, 65), (1, 1025)])
 def test_vit_noncausal_packed_qkv(N, S):
     from vita_b200 import ops

@@ -63,14 +63,14 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) {
     return static_cast<uint32_t>(row * D * 2 + ((chunk ^ (row & 7)) << 4));
 }
 
-template <int D>
+template <int D, int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_bfloat16* g, long long tok_stride,
                                                 int row0, int n_valid_rows) {
     constexpr int CPR = D / 8;  // chunks per row
-    constexpr int TOTAL = 64 * CPR;
+    constexpr int TOTAL = ROWS * CPR;
 #pragma unroll
-    for (int i = 0; i < TOTAL / 128; ++i) {
-        const int c = threadIdx.x + i * 128;
+    for (int i = 0; i < TOTAL / THREADS; ++i) {
+        const int c = threadIdx.x + i * THREADS;
         const int r = c / CPR, ch = c % CPR;
         const bool ok = (row0 + r) < n_valid_rows;
         const __nv_bfloat16* src = g + static_cast<long long>(ok ? (row0 + r) : 0) * tok_stride + ch * 8;
@@ -78,12 +78,15 @@ __device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_b
     }
 }
 
-template <int DQK, int DV>
-__global__ void __launch_bounds__(128)
+// BM query rows per CTA (BM / 16 warps); K/V tiles of 64 keys.  BM = 128 halves the K/V shared-memory traffic per FLOP
+// (used for long sequences), BM = 64 keeps enough CTAs in flight for short ones.
+template <int DQK, int DV, int BM>
+__global__ void __launch_bounds__(BM * 2)
 flash_fwd_kernel(const AttnParams p) {
+    constexpr int THREADS = BM * 2;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);
-    const uint32_t sK = sQ + 64 * DQK * 2;
+    const uint32_t sK = sQ + BM * DQK * 2;
     const uint32_t sV = sK + 2 * 64 * DQK * 2;
 
     const int m_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -91,18 +94,18 @@ flash_fwd_kernel(const AttnParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int kv_len = p.kv_lens ? p.kv_lens[b] : p.Skv;
     if (kv_len > p.Skv) kv_len = p.Skv;
-    const int q0 = m_blk * 64;
+    const int q0 = m_blk * BM;
     int n_tiles = (kv_len + 63) / 64;
-    if (p.causal && n_tiles > m_blk + 1) n_tiles = m_blk + 1;
+    if (p.causal && n_tiles > (q0 + BM + 63) / 64) n_tiles = (q0 + BM + 63) / 64;
 
     const __nv_bfloat16* qg = p.q + b * p.q_bs + head * p.q_hs;
     const __nv_bfloat16* kg = p.k + b * p.k_bs + kvh * p.k_hs;
     const __nv_bfloat16* vg = p.v + b * p.v_bs + kvh * p.v_hs;
 
-    load_tile_async<DQK>(sQ, qg, p.q_ts, q0, p.Sq);
+    load_tile_async<DQK, BM, THREADS>(sQ, qg, p.q_ts, q0, p.Sq);
     if (n_tiles > 0) {
-        load_tile_async<DQK>(sK, kg, p.k_ts, 0, kv_len);
-        load_tile_async<DV>(sV, vg, p.v_ts, 0, kv_len);
+        load_tile_async<DQK, 64, THREADS>(sK, kg, p.k_ts, 0, kv_len);
+        load_tile_async<DV, 64, THREADS>(sV, vg, p.v_ts, 0, kv_len);
     }
     cp_async_commit();
 
@@ -121,8 +124,8 @@ flash_fwd_kernel(const AttnParams p) {
     for (int j = 0; j < n_tiles; ++j) {
         const int buf = j & 1;
         if (j + 1 < n_tiles) {
-            load_tile_async<DQK>(sK + (buf ^ 1) * 64 * DQK * 2, kg, p.k_ts, (j + 1) * 64, kv_len);
-            load_tile_async<DV>(sV + (buf ^ 1) * 64 * DV * 2, vg, p.v_ts, (j + 1) * 64, kv_len);
+            load_tile_async<DQK, 64, THREADS>(sK + (buf ^ 1) * 64 * DQK * 2, kg, p.k_ts, (j + 1) * 64, kv_len);
+            load_tile_async<DV, 64, THREADS>(sV + (buf ^ 1) * 64 * DV * 2, vg, p.v_ts, (j + 1) * 64, kv_len);
         }
         cp_async_commit();
         cp_async_wait<1>();
@@ -236,20 +239,28 @@ flash_fwd_kernel(const AttnParams p) {
     }
 }
 
-template <int DQK, int DV>
-static int launch_flash(const AttnParams& p, int B, int Hq, cudaStream_t st) {
-    constexpr int smem_bytes = 64 * DQK * 2 + 2 * 64 * DQK * 2 + 2 * 64 * DV * 2;
+template <int DQK, int DV, int BM>
+static int launch_flash_bm(const AttnParams& p, int B, int Hq, cudaStream_t st) {
+    constexpr int smem_bytes = BM * DQK * 2 + 2 * 64 * DQK * 2 + 2 * 64 * DV * 2;
     static bool configured = false;
-    auto kern = flash_fwd_kernel<DQK, DV>;
+    auto kern = flash_fwd_kernel<DQK, DV, BM>;
     if (!configured) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
                             "cudaFuncSetAttribute(flash smem)");
         if (rc) return rc;
         configured = true;
     }
-    dim3 grid((p.Sq + 63) / 64, Hq, B);
-    kern<<<grid, 128, smem_bytes, st>>>(p);
+    dim3 grid((p.Sq + BM - 1) / BM, Hq, B);
+    kern<<<grid, BM * 2, smem_bytes, st>>>(p);
     return check_launch("flash_fwd_kernel");
+}
+
+template <int DQK, int DV>
+static int launch_flash(const AttnParams& p, int B, int Hq, cudaStream_t st) {
+    // 128-row CTAs once they still fill the machine twice over
+    const long long ctas128 = static_cast<long long>((p.Sq + 127) / 128) * Hq * B;
+    if (ctas128 >= 2ll * num_sms()) return launch_flash_bm<DQK, DV, 128>(p, B, Hq, st);
+    return launch_flash_bm<DQK, DV, 64>(p, B, Hq, st);
 }
 
 // ------------------------------------------------------------------------------------------------ paged decode

@@ -650,9 +650,29 @@ __global__ void decode_slots_kernel(const int* __restrict__ cur_pos, const int* 
     slots[b] = block_table[static_cast<long long>(b) * max_pages + pos / page_size] * page_size + pos % page_size;
 }
 
+// L2 prefetch of a weight matrix (cp.async.bulk.prefetch.L2): lets the o-projection weights arrive while the
+// (latency-bound) decode attention runs, so the o-projection GEMV then streams from L2.
+__global__ void l2_prefetch_kernel(const char* __restrict__ base, long long bytes) {
+    const long long chunk = 64 * 1024;
+    const long long n_chunks = (bytes + chunk - 1) / chunk;
+    for (long long c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long off = c * chunk;
+        const unsigned int sz = static_cast<unsigned int>((bytes - off < chunk ? bytes - off : chunk) & ~15ll);
+        if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
+    }
+}
+
 }  // namespace vita
 
 using namespace vita;
+
+extern "C" int vita_l2_prefetch(const void* ptr, int64_t bytes, void* stream) {
+    VITA_REQUIRE(aligned16(ptr), "pointer must be 16-byte aligned");
+    if (bytes <= 0) return VITA_OK;
+    l2_prefetch_kernel<<<num_sms() > 0 ? num_sms() : 1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const char*>(ptr), bytes);
+    return check_launch("l2_prefetch");
+}
 
 extern "C" int vita_argmax_rows(const void* logits, uint64_t* best, int64_t B, int64_t V, void* stream) {
     if (B == 0) return VITA_OK;

@@ -79,6 +79,9 @@ class MixtralDecoder:
         max_rb = max((cfg.vocab_size + 127) // 128, 2 * (I // 128), cfg.num_attention_heads
                      + 2 * cfg.num_key_value_heads, (H + 127) // 128)
         self.tc_ws = ops.TcWorkspace(B, max_rb, dev) if self.use_tc else None
+        # L2 prefetch of the o-projection weights during the decode attention (VITA_B200_L2PF=1)
+        self.l2_prefetch = os.environ.get("VITA_B200_L2PF", "0") == "1"
+        self._side = torch.cuda.Stream(device=dev) if self.l2_prefetch else None
         # single-kernel decode step (bs = 1): VITA_B200_DECODE=mega
         self.mega = None
         if os.environ.get("VITA_B200_DECODE", "kernels") == "mega" and self.use_tc and weights.get("ep", (0, 1))[1] == 1:
@@ -256,7 +259,13 @@ class MixtralDecoder:
                            cache.block_table[:1], cache.page_size, c.rms_norm_eps, D ** -0.5)
             return
         tc, ws = self.use_tc, self.tc_ws
+        l2pf = self.l2_prefetch
+        main = torch.cuda.current_stream()
         for li, lw in enumerate(w["layers"]):
+            if l2pf:
+                # side stream: once the previous layer's down projection is done streaming... the o-proj weights can
+                # come into L2 while qkv + attention (both far from saturating HBM) run
+                pass
             if tc:
                 ops.decode_tc_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
                                        self.d_q[:B], cache.k[li], cache.v[li], ws, nq, nkv, D, cache.page_size,
@@ -264,6 +273,12 @@ class MixtralDecoder:
             else:
                 ops.decode_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
                                     self.d_q[:B], cache.k[li], cache.v[li], nq, nkv, D, cache.page_size, c.rms_norm_eps)
+            if l2pf:
+                ev = torch.cuda.Event()
+                ev.record(main)                       # after the qkv kernel: HBM is idle during attention
+                self._side.wait_event(ev)
+                with torch.cuda.stream(self._side):
+                    ops.l2_prefetch(lw["wo"])
             ops.decode_attention(self.d_q[:B], cache.k[li], cache.v[li], cache.block_table[:B], cache.cur_pos[:B],
                                  self.d_attn[:B], self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits,
                                  D ** -0.5)
@@ -277,6 +292,8 @@ class MixtralDecoder:
                 ops.decode_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B],
                                        self.d_act[:B], c.rms_norm_eps)
                 ops.decode_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h)
+        if l2pf:
+            main.wait_stream(self._side)             # join (required to end a graph capture)
         lg = self.d_logits[:B] if want_logits else None
         if tc:
             ops.tc_lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, ws, c.rms_norm_eps)

@@ -140,6 +140,10 @@ def decode_slots(cur_pos, block_table, slots, page_size):
               block_table.shape[1], _stream())
 
 
+def l2_prefetch(t: torch.Tensor):
+    _lib.call("vita_l2_prefetch", _p(t), t.numel() * t.element_size(), _stream())
+
+
 def argmax_rows(logits, best):
     _chk(logits, BF16, "logits"); _chk(best, torch.int64, "best")
     _lib.call("vita_argmax_rows", _p(logits), _p(best), logits.shape[0], logits.shape[1], _stream())
