@@ -57,7 +57,7 @@ class MixtralDecoder:
         assert max_seq_len <= weights["rope"].shape[0], "rope table too short for max_seq_len"
         self.cache = PagedKVCache(cfg, max_batch, max_seq_len, device, page_size, shuffle_pages)
         self.max_new_tokens = max_new_tokens
-        self.decode_splits = decode_splits
+        self.decode_splits = int(os.environ.get("VITA_B200_ATTN_SPLITS", decode_splits))
         H, I = cfg.hidden_size, cfg.intermediate_size
         B = max_batch
         dev = self.device
@@ -73,7 +73,7 @@ class MixtralDecoder:
         self.d_w = torch.zeros(B, 2, dtype=torch.float32, device=dev)
         self.d_act = torch.zeros(B, 2, I, dtype=BF16, device=dev)
         self.d_logits = torch.zeros(B, cfg.vocab_size, dtype=BF16, device=dev)
-        self.attn_ws = ops.decode_attention_workspace(B, cfg.num_key_value_heads, decode_splits, dev)
+        self.attn_ws = ops.decode_attention_workspace(B, cfg.num_key_value_heads, self.decode_splits, dev)
         # decode linears: tcgen05 swap-AB GEMV (default) or the SIMT streaming GEMV (VITA_B200_GEMV=simt)
         self.use_tc = os.environ.get("VITA_B200_GEMV", "tc") != "simt" and H % 64 == 0 and I % 128 == 0
         max_rb = max((cfg.vocab_size + 127) // 128, 2 * (I // 128), cfg.num_attention_heads
@@ -87,7 +87,7 @@ class MixtralDecoder:
         if os.environ.get("VITA_B200_DECODE", "kernels") == "mega" and self.use_tc and weights.get("ep", (0, 1))[1] == 1:
             self.mega = ops.MegaDecode(weights["layers"], weights["lm_head"], self.cache.k, self.cache.v, H, I,
                                        cfg.num_local_experts, cfg.num_attention_heads, cfg.num_key_value_heads,
-                                       cfg.vocab_size, decode_splits, dev)
+                                       cfg.vocab_size, self.decode_splits, dev)
         self._graph = None
         self._graph_batch = None
         self._bgraph = None
