@@ -188,7 +188,6 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -207,6 +206,9 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
                                 op.a_row(b, rb, p, sm));
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            // all of this CTA's weight loads are issued: with programmatic dependent launch the next kernel of the
+            // chain may now take the free half of the SM and fill its ring while this CTA drains and reduces
+            pdl_launch_dependents();
         }
     } else if (warp == 1) {
         if (lane == 0) {
