@@ -38,6 +38,11 @@ const char* vita_last_error(void);
 int vita_num_sms(void);
 /* counts kernels launched through this library since the last reset (bench.py's gpu_launches) */
 int64_t vita_launch_count(int reset);
+/* Tunables (each also has an environment default): "pdl", "attn_early", "chain_wait",
+ * "tc_prefetch_consts", "tc_wide_route", "tc_l2_ahead", "tc_trigger_lead".
+ * Takes effect for launches issued afterwards (a captured CUDA graph keeps what it was captured with). */
+int vita_set_option(const char* name, int64_t value);
+int64_t vita_get_option(const char* name);
 
 /* ---- dense linear:  C[M,N] = residual + colscale * act(A[M,K] . B[N,K]^T + bias) ----------------------------
  * tcgen05 / TMEM / TMA GEMM.  Replaces nn.Linear -> cuBLAS at
@@ -191,7 +196,10 @@ int vita_l2_prefetch(const void* ptr, int64_t bytes, void* stream);
  * Same operations and epilogues as the vita_decode_* entry points above, with the weight tile as the M operand of
  * tcgen05.mma and the activation vector as row 0 of a 16-wide N operand; (row-block, k-block) units are split evenly
  * over all SMs and combined through `workspace` (vita_decode_tc_workspace_bytes, zero-initialised once, shared by all
- * five calls; ws_row_blocks = the max_row_blocks it was sized for).  K multiples of 64. */
+ * five calls; ws_row_blocks = the max_row_blocks it was sized for): K-partials travel as 64-bit {value, tag} words,
+ * the CTA that ends on a row block adds them in slot order (deterministic) and clears the tags.  K multiples of 64.
+ * With programmatic dependent launch ("pdl") each kernel triggers its successor once its last weight tile is issued
+ * and the successor fills its shared-memory ring before the dependency wait. */
 int64_t vita_decode_tc_workspace_bytes(int64_t B, int64_t max_row_blocks);
 int vita_decode_tc_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, const float* cos_sin,
                             const int32_t* cur_pos, const int32_t* block_table, void* q_out, void* k_cache,

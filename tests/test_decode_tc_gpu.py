@@ -1,5 +1,5 @@
-"""Decode-step linears on tcgen05 (swap-AB GEMV, stream-K partial slots) vs the oracle's functions.
-Each kernel is launched twice on the same workspace to exercise the self-resetting tickets."""
+"""Decode-step linears on tcgen05 (swap-AB GEMV, stream-K with tagged partial slots) vs the oracle's functions.
+Each kernel is launched twice on the same workspace to exercise the self-clearing slot tags."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -124,3 +124,66 @@ def test_tc_lm_head_argmax(H, V):
         for b in range(B):
             first = int((lg[b] == lg[b].max()).nonzero()[0])
             assert int(got_idx[b]) == first
+
+
+@pytest.fixture
+def tc_options():
+    """Sets library tunables for one test and restores the defaults afterwards."""
+    from vita_b200 import ops
+    names = ("tc_wide_route", "tc_l2_ahead", "tc_trigger_lead", "pdl")
+    before = {n: ops.get_option(n) for n in names}
+    yield ops.set_option
+    for n, v in before.items():
+        ops.set_option(n, v)
+
+
+def _moe_pair(ops, h, nw, gw, w13, w2, ws, I):
+    B = h.shape[0]
+    hd = h.clone()
+    act = torch.empty(B, 2, I, dtype=BF16, device="cuda")
+    ids = torch.full((B, 2), -1, dtype=torch.int32, device="cuda")
+    tw = torch.zeros(B, 2, dtype=torch.float32, device="cuda")
+    ops.decode_tc_moe_gate_up(hd, nw, gw, w13, ids, tw, act, ws, 1e-5)
+    ops.decode_tc_moe_down(act, w2, ids, tw, hd, ws)
+    return hd, act, ids, tw
+
+
+def test_tc_tunables_keep_the_bits(tc_options):
+    """Programmatic launch, the L2 look-ahead and the trigger placement only move work in time: outputs must be
+    bit-identical.  The wide router changes the summation order of the 8 logits, so the narrow one is held to the same
+    expert choice and to float tolerance on the weights."""
+    from vita_b200 import ops
+    B, H, I, E, V = 2, 4096, 14336, 8, 51760
+    h = to_dev(randn((B, H), 1, 1.5))
+    nw, gw = to_dev(randn((H,), 2)), to_dev(randn((E, H), 3, 0.05))
+    w13, w2 = _gpu_randn((E, 2 * I, H), 4, 0.03), _gpu_randn((E, H, I), 5, 0.03)
+    wo = _gpu_randn((H, H), 6, 0.03)
+    wl = _gpu_randn((V, H), 7, 0.03)
+    x = to_dev(randn((B, H), 8))
+    ws = _ws(B, max(2 * (I // 128), (V + 127) // 128))
+
+    def run_all():
+        out = list(_moe_pair(ops, h, nw, gw, w13, w2, ws, I))
+        ho = h.clone()
+        ops.decode_tc_oproj(x, wo, ho, ws)
+        out.append(ho)
+        logits = torch.empty(B, V, dtype=BF16, device="cuda")
+        best = torch.zeros(B, dtype=torch.int64, device="cuda")
+        ops.tc_lm_head_argmax(h, H, nw, wl, logits, best, B, ws, 1e-5)
+        out += [logits, best.clone()]
+        return out
+
+    base = run_all()
+    for name, value, restore in (("pdl", 0, 1), ("tc_l2_ahead", 6, 0), ("tc_trigger_lead", 3, 0)):
+        tc_options(name, value)
+        for rep in range(2):
+            got = run_all()
+            for a, b in zip(base, got):
+                assert torch.equal(a, b), f"{name}={value} changed an output (rep {rep})"
+        tc_options(name, restore)
+    tc_options("tc_wide_route", 0)
+    hd, act, ids, tw = _moe_pair(ops, h, nw, gw, w13, w2, ws, I)
+    assert torch.equal(ids, base[2])
+    assert (tw - base[3]).abs().max() < 1e-5
+    assert_close(act, base[1], rel=1e-3, what="narrow-router activations")
+    assert_close(hd, base[0], rel=1e-3, what="narrow-router MoE output")

@@ -21,6 +21,8 @@ SIGNATURES = {
     "vita_last_error": (c_char_p, []),
     "vita_num_sms": (c_int, []),
     "vita_launch_count": (I64, [c_int]),
+    "vita_set_option": (c_int, [ctypes.c_char_p, I64]),
+    "vita_get_option": (I64, [ctypes.c_char_p]),
     "vita_gemm_bf16": (c_int, [P, I64, P, P, I64, I64, I64, I64, P, c_int, P, P, I64, P]),
     "vita_rmsnorm": (c_int, [P, P, P, I64, I64, c_float, P]),
     "vita_layernorm": (c_int, [P, P, P, P, I64, I64, c_float, c_int, c_float, P]),

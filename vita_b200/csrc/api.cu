@@ -37,14 +37,65 @@ int num_sms() {
     return cached;
 }
 
-bool use_pdl() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("VITA_B200_PDL");
-        cached = (e != nullptr && e[0] == '1') ? 1 : 0;   // measured: no gain (5.27 ms/token off vs 5.31 on) -> opt-in
+// Tunables: default <- environment variable (read once) <- vita_set_option().
+struct Option {
+    const char* name;
+    const char* env;
+    int def;
+    std::atomic<int> value;
+};
+static Option g_options[] = {
+    // programmatic dependent launch for the decode chain (trigger after each CTA's last weight load)
+    {"pdl", "VITA_B200_PDL", 1, {-1}},
+    // tcgen05 decode kernels: weight tiles per CTA prefetched into L2 behind the shared-memory ring
+    {"tc_l2_ahead", "VITA_B200_TC_L2AHEAD", 0, {-1}},
+    // paged decode attention: fetch the cached K/V rows ahead of the dependency wait (needs chain_wait)
+    {"attn_early", "VITA_B200_ATTN_EARLY", 1, {-1}},
+    // chain kernels wait for their predecessor before they trigger their successor: when kernel N+1 starts, kernel
+    // N-1 has completed (what attn_early relies on)
+    {"chain_wait", "VITA_B200_CHAIN_WAIT", 1, {-1}},
+    // tcgen05 gate|up kernel: all 256 threads share the router dot products
+    {"tc_wide_route", "VITA_B200_TC_WIDE_ROUTE", 1, {-1}},
+    // tcgen05 decode kernels: weight tiles still to be issued by a CTA when it triggers the dependent launch
+    {"tc_trigger_lead", "VITA_B200_TC_TRIGGER_LEAD", 0, {-1}},
+    // tcgen05 decode kernels: pull norm / router weights into L2 ahead of the dependency wait
+    {"tc_prefetch_consts", "VITA_B200_TC_PREFETCH_CONSTS", 1, {-1}},
+};
+
+int option(const char* name) {
+    for (Option& o : g_options) {
+        if (std::string(o.name) != name) continue;
+        int v = o.value.load(std::memory_order_relaxed);
+        if (v < 0) {
+            const char* e = getenv(o.env);
+            v = (e != nullptr && e[0] != '\0') ? atoi(e) : o.def;
+            if (v < 0) v = 0;
+            o.value.store(v, std::memory_order_relaxed);
+        }
+        return v;
     }
-    return cached == 1;
+    return 0;
 }
+
+bool use_pdl() { return option("pdl") != 0; }
+
+}  // namespace vita
+
+extern "C" int vita_set_option(const char* name, int64_t value) {
+    VITA_REQUIRE(name != nullptr && value >= 0, "vita_set_option: name and a non-negative value are required");
+    for (vita::Option& o : vita::g_options) {
+        if (std::string(o.name) == name) {
+            o.value.store(static_cast<int>(value), std::memory_order_relaxed);
+            return VITA_OK;
+        }
+    }
+    vita::set_last_error(std::string("vita_set_option: unknown option '") + name + "'");
+    return VITA_ERR_INVALID;
+}
+
+extern "C" int64_t vita_get_option(const char* name) { return name ? vita::option(name) : 0; }
+
+namespace vita {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -280,7 +280,15 @@ struct DecodeAttnParams {
     int* tickets;                  // [B, n_kv], zero-initialised, self-resetting
     int n_q, n_kv, page_size, max_pages, splits;
     float scale_log2;
+    int early;                     // fetch cached K/V rows before the dependency wait
 };
+
+// ordered 16-byte load: volatile asm keeps it on its side of the dependency wait
+__device__ __forceinline__ uint4 ld_early_v4(const void* ptr) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+    return r;
+}
 
 __global__ void __launch_bounds__(128)
 decode_attn_kernel(const DecodeAttnParams p) {
@@ -291,8 +299,14 @@ decode_attn_kernel(const DecodeAttnParams p) {
 
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
     pdl_launch_dependents();
-    pdl_wait();   // q and the newest K/V row come from the QKV kernel
+    if (!p.early) pdl_wait();
+    // ---- before the dependency wait -------------------------------------------------------------------------------
+    // cur_pos (first kernel of the step), the block table and every cached K/V row except the newest one are NOT
+    // written by the kernel right before this one (the QKV projection of this layer), and the kernel before that has
+    // completed by the time this grid could be launched (each chain kernel waits before it triggers).  So with
+    // programmatic dependent launch the old keys are already in registers when the QKV kernel retires.
     const int ctx = p.cur_pos[b] + 1;
+    const int newest = ctx - 1;
     const int per = (ctx + p.splits - 1) / p.splits;
     const int k_begin = split * per;
     const int k_end = min(ctx, k_begin + per);
@@ -300,6 +314,43 @@ decode_attn_kernel(const DecodeAttnParams p) {
     const int lg = threadIdx.x >> 3;  // lane group 0..15: one key at a time
     const int sl = threadIdx.x & 7;   // 16 dims per lane
     const int d0 = sl * 16;
+    const int* bt = p.block_table + static_cast<long long>(b) * p.max_pages;
+
+    constexpr int NPRE = 4;           // keys per lane group fetched up front (covers ctx <= splits * 64)
+    uint4 pk[NPRE][2], pv[NPRE][2];
+    long long pslot[NPRE];
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+        const int key = k_begin + j * 16 + lg;
+        pslot[j] = -1;
+        if (key < k_end) {
+            const int page = bt[key / p.page_size];
+            pslot[j] = static_cast<long long>(page) * p.page_size + key % p.page_size;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+        const int key = k_begin + j * 16 + lg;
+        if (pslot[j] >= 0 && key != newest) {
+            const __nv_bfloat16* kp = p.k_cache + (pslot[j] * p.n_kv + kvh) * DEC_D + d0;
+            const __nv_bfloat16* vp = p.v_cache + (pslot[j] * p.n_kv + kvh) * DEC_D + d0;
+            pk[j][0] = ld_early_v4(kp); pk[j][1] = ld_early_v4(kp + 8);
+            pv[j][0] = ld_early_v4(vp); pv[j][1] = ld_early_v4(vp + 8);
+        } else {
+            pk[j][0] = pk[j][1] = pv[j][0] = pv[j][1] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    pdl_wait();   // q and the newest K/V row come from the QKV kernel
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+        const int key = k_begin + j * 16 + lg;
+        if (pslot[j] >= 0 && key == newest) {
+            const __nv_bfloat16* kp = p.k_cache + (pslot[j] * p.n_kv + kvh) * DEC_D + d0;
+            const __nv_bfloat16* vp = p.v_cache + (pslot[j] * p.n_kv + kvh) * DEC_D + d0;
+            pk[j][0] = ld_early_v4(kp); pk[j][1] = ld_early_v4(kp + 8);
+            pv[j][0] = ld_early_v4(vp); pv[j][1] = ld_early_v4(vp + 8);
+        }
+    }
 
     float q[DEC_GROUP][16];
 #pragma unroll
@@ -318,26 +369,8 @@ decode_attn_kernel(const DecodeAttnParams p) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[h][i] = 0.0f;
     }
-    const int* bt = p.block_table + static_cast<long long>(b) * p.max_pages;
-    // software pipeline: the K/V rows of the next key are in flight while the current one is reduced
-    uint4 nk0, nk1, nv0, nv1;
-    auto issue = [&](int key) {
-        if (key < k_end) {
-            const int page = bt[key / p.page_size];
-            const long long slot = static_cast<long long>(page) * p.page_size + key % p.page_size;
-            const uint4* kp = reinterpret_cast<const uint4*>(p.k_cache + (slot * p.n_kv + kvh) * DEC_D + d0);
-            const uint4* vp = reinterpret_cast<const uint4*>(p.v_cache + (slot * p.n_kv + kvh) * DEC_D + d0);
-            nk0 = kp[0]; nk1 = kp[1]; nv0 = vp[0]; nv1 = vp[1];
-        } else {
-            nk0 = nk1 = nv0 = nv1 = make_uint4(0, 0, 0, 0);
-        }
-    };
-    issue(k_begin + lg);
-    for (int key0 = k_begin; key0 < k_end; key0 += 16) {  // trip count is uniform across the warp (shuffles below)
-        const int key = key0 + lg;
-        const bool valid = key < k_end;
-        const uint4 ka = nk0, kc = nk1, va = nv0, vc = nv1;
-        issue(key + 16);
+    // one key per lane group: scores for the 4 query heads of this kv head, online softmax, P.V
+    auto consume = [&](const uint4& ka, const uint4& kc, const uint4& va, const uint4& vc, bool valid) {
         const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kc.x, kc.y, kc.z, kc.w};
         const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vc.x, vc.y, vc.z, vc.w};
         float kf[16], vf[16];
@@ -364,6 +397,34 @@ decode_attn_kernel(const DecodeAttnParams p) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) acc[h][i] = acc[h][i] * alpha + pr * vf[i];
             }
+        }
+    };
+    const int n_keys = max(k_end - k_begin, 0);
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+        if (j * 16 < n_keys)   // uniform across the CTA (shuffles inside)
+            consume(pk[j][0], pk[j][1], pv[j][0], pv[j][1], pslot[j] >= 0);
+    }
+    // longer contexts: software pipeline, the K/V rows of the next key are in flight while the current one is reduced
+    if (n_keys > NPRE * 16) {
+        uint4 nk0, nk1, nv0, nv1;
+        auto issue = [&](int key) {
+            if (key < k_end) {
+                const int page = bt[key / p.page_size];
+                const long long slot = static_cast<long long>(page) * p.page_size + key % p.page_size;
+                const uint4* kp = reinterpret_cast<const uint4*>(p.k_cache + (slot * p.n_kv + kvh) * DEC_D + d0);
+                const uint4* vp = reinterpret_cast<const uint4*>(p.v_cache + (slot * p.n_kv + kvh) * DEC_D + d0);
+                nk0 = kp[0]; nk1 = kp[1]; nv0 = vp[0]; nv1 = vp[1];
+            } else {
+                nk0 = nk1 = nv0 = nv1 = make_uint4(0, 0, 0, 0);
+            }
+        };
+        issue(k_begin + NPRE * 16 + lg);
+        for (int key0 = k_begin + NPRE * 16; key0 < k_end; key0 += 16) {  // trip count is uniform across the warp
+            const int key = key0 + lg;
+            const uint4 ka = nk0, kc = nk1, va = nv0, vc = nv1;
+            issue(key + 16);
+            consume(ka, kc, va, vc, key < k_end);
         }
     }
     // merge the 16 lane groups of this CTA
@@ -495,6 +556,7 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
     p.n_q = (int)n_q_heads; p.n_kv = (int)n_kv_heads; p.page_size = (int)page_size; p.max_pages = (int)max_pages;
     p.splits = (int)splits;
     p.scale_log2 = scale * 1.4426950408889634f;
+    p.early = option("attn_early");
     dim3 grid((unsigned)splits, (unsigned)n_kv_heads, (unsigned)B);
     cudaError_t e = launch_chain(decode_attn_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p);
     if (e != cudaSuccess) return check_cuda(e, "decode_attn_kernel");

@@ -41,6 +41,7 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
 // N drains; it calls griddepcontrol.wait before touching anything N produced.  Opt-in with VITA_B200_PDL=1: on B200
 // it measured neutral with 1 CTA/SM footprints and 12% slower when the footprints allowed co-residency.
 bool use_pdl();
+int option(const char* name);   // tunables table in api.cu (env default, vita_set_option override)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

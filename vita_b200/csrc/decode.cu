@@ -126,7 +126,6 @@ stream_gemv_kernel(const Op op) {
         fence_barrier_init();
     }
     __syncthreads();
-    pdl_launch_dependents();   // the next kernel of the decode chain may start filling its weight ring
 
     if (warp == GV_CONSUMERS / 32) {
         if (lane == 0) {
@@ -147,6 +146,10 @@ stream_gemv_kernel(const Op op) {
                     if (++stage == GV_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            // every weight load of this CTA is issued: the next kernel of the chain may start filling its ring.
+            // Waiting first keeps the chain transitive (when kernel N+1 starts, kernel N-1 is complete).
+            pdl_wait();
+            pdl_launch_dependents();
         }
         return;
     }

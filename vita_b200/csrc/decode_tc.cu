@@ -31,6 +31,14 @@ __device__ __forceinline__ void tmem_ld_32x32_x1(uint32_t taddr, uint32_t& r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // sum over the 128 epilogue threads (warps 4..7); scratch >= 4 floats
 __device__ __forceinline__ float epi_sum(float v, float* scratch) {
@@ -112,6 +120,91 @@ __device__ __forceinline__ void tc_load_x_rmsnorm(const __nv_bfloat16* h, const 
         *reinterpret_cast<uint4*>(xs + i) = o;
     }
 }
+// RMSNorm statistics + the 8 router logits of one token, by the 128 epilogue threads (fp32 throughout, soft-max and
+// top-2 as the reference's MixtralSparseMoeBlock).  Every caller gets the same bits: same loads, same summation order.
+struct TcRoute {
+    int e0, e1;
+    float w0, w1;   // renormalised top-2 weights
+    float inv;      // 1 / rms(h)
+};
+// per-thread partial sums over this thread's share of the K axis: [0] = sum h^2, [1 + e] = sum h * norm_w * gate_w[e]
+__device__ __forceinline__ void tc_route_partials(const __nv_bfloat16* hr, const __nv_bfloat16* norm_w,
+                                                  const __nv_bfloat16* gate_w, int K, int tid, int nthreads,
+                                                  float (&part)[9]) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) part[e] = 0.0f;
+#pragma unroll 2
+    for (int i = tid * 8; i < K; i += nthreads * 8) {
+        const uint4 hv = *reinterpret_cast<const uint4*>(hr + i);
+        const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w + i));
+        uint4 ge[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ge[e] = __ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * K + i));
+        const uint32_t a[4] = {hv.x, hv.y, hv.z, hv.w}, gg[4] = {g.x, g.y, g.z, g.w};
+        float xw[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float lo = bf16_lo(a[q]), hi = bf16_hi(a[q]);
+            part[0] += lo * lo + hi * hi;
+            xw[2 * q] = lo * bf16_lo(gg[q]);
+            xw[2 * q + 1] = hi * bf16_hi(gg[q]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t w[4] = {ge[e].x, ge[e].y, ge[e].z, ge[e].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) part[1 + e] += xw[2 * q] * bf16_lo(w[q]) + xw[2 * q + 1] * bf16_hi(w[q]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) part[e] = warp_sum(part[e]);
+}
+// soft-max over the 8 logits, top-2, renormalised weights (fp32; MixtralSparseMoeBlock order of operations)
+__device__ __forceinline__ TcRoute tc_route_finish(const float (&tot)[9], int K, float eps) {
+    TcRoute r;
+    r.inv = rsqrtf(tot[0] / static_cast<float>(K) + eps);
+    float p[8], m = -INFINITY, sum = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { p[e] = tot[1 + e] * r.inv; m = fmaxf(m, p[e]); }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { p[e] = expf(p[e] - m); sum += p[e]; }
+    int e0 = 0;
+#pragma unroll
+    for (int e = 1; e < 8; ++e) if (p[e] > p[e0]) e0 = e;
+    int e1 = (e0 == 0) ? 1 : 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if (e != e0 && p[e] > p[e1]) e1 = e;
+    float pe0 = 0.0f, pe1 = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { if (e == e0) pe0 = p[e]; if (e == e1) pe1 = p[e]; }
+    const float p0 = pe0 / sum, p1 = pe1 / sum, den = p0 + p1;
+    r.e0 = e0; r.e1 = e1; r.w0 = p0 / den; r.w1 = p1 / den;
+    return r;
+}
+// narrow form: the 128 epilogue threads do everything
+__device__ __forceinline__ TcRoute tc_route(const __nv_bfloat16* hr, const __nv_bfloat16* norm_w,
+                                            const __nv_bfloat16* gate_w, int K, float eps, float* prep) {
+    float part[9];
+    tc_route_partials(hr, norm_w, gate_w, K, threadIdx.x - 128, 128, part);
+    const int w4 = (threadIdx.x >> 5) - 4;
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int e = 0; e < 9; ++e) prep[w4 * 9 + e] = part[e];
+    epi_barrier();
+    float tot[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) tot[e] = prep[e] + prep[9 + e] + prep[18 + e] + prep[27 + e];
+    epi_barrier();   // prep may be reused by the caller
+    return tc_route_finish(tot, K, eps);
+}
+// Pull constant tensors into L2 while the kernel is still waiting for its predecessor (CTA-sharded, 128 B lines).
+__device__ __forceinline__ void tc_prefetch_l2(const void* base, long long bytes) {
+    const long long lines = (bytes + 127) / 128;
+    for (long long l = static_cast<long long>(blockIdx.x) * 128 + (threadIdx.x - 128); l < lines;
+         l += static_cast<long long>(gridDim.x) * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const char*>(base) + l * 128));
+}
+
 // Plain copy of an activation vector: one TMA 1-D bulk copy that completes straight onto the x_ready barrier.
 __device__ __forceinline__ void tc_bulk_x(const __nv_bfloat16* src, __nv_bfloat16* xs, int n, uint64_t* bar) {
     if (threadIdx.x == 128) {
@@ -130,9 +223,12 @@ struct TcFinish {
 // PARTS: weight tiles per unit (1, or 2 for gate|up and for the two experts of the down projection).
 // XPARTS: distinct activation vectors (2 only for the down projection).
 template <class Op>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __restrict__ g_scratch,
-               int* __restrict__ g_tickets) {
+#ifndef TC_MIN_BLOCKS
+#define TC_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(TC_THREADS, TC_MIN_BLOCKS)
+tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned long long* __restrict__ g_scratch,
+               const int l2_ahead, const int flags) {
     constexpr int PARTS = Op::kParts, XPARTS = Op::kXParts, STAGES = Op::kStages;
     constexpr int STAGE_A = PARTS * TC_A_BYTES;
     constexpr int STAGE_X = XPARTS * TC_X_BYTES;
@@ -189,6 +285,16 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // router-carrying op, wide form: every thread of the CTA takes part in the router dot products before the roles
+    // split up (the producer cannot start without the expert ids anyway)
+    const bool wide = Op::kHasRoute && (flags & 8) != 0;
+    if (wide) {
+        if (warp >= 4) op.pre_wait(b, sm, (flags & 1) != 0);
+        pdl_wait();
+        op.wide_partials(b, sm);
+        __syncthreads();
+    }
+
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer (weights)
@@ -196,7 +302,17 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
             else if (Op::kRowsNeedUpstream) pdl_wait();                 // expert ids written by the previous kernel
             int stage = 0;
             uint32_t phase = 0;
+            // With programmatic dependent launch the next kernel of the chain may take the free half of the SM and fill
+            // its ring while this CTA drains and reduces: trigger once all but `lead` of this CTA's loads are issued.
+            // Waiting first (long since satisfied) makes the chain transitive: when kernel N+1 starts, N-1 is complete.
+            const int lead = flags >> 8;
+            bool triggered = false;
             for (long long u = u0; u < u1; ++u) {
+                if (!triggered && u1 - u <= lead) {
+                    if ((flags & 2) && u > u0) pdl_wait();
+                    pdl_launch_dependents();
+                    triggered = true;
+                }
                 const int rb = static_cast<int>(u / n_kb), kb = static_cast<int>(u % n_kb);
                 mbar_wait(&empty_bar[stage], phase ^ 1, 22);
                 mbar_arrive_expect_tx(&full_bar[stage], STAGE_A);
@@ -205,10 +321,20 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
                     tma_load_2d(sA + stage * STAGE_A + p * TC_A_BYTES, &tmW, &full_bar[stage], kb * 64,
                                 op.a_row(b, rb, p, sm));
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (l2_ahead > 0 && u - u0 == STAGES - 1) {
+                    // the ring is full and (under programmatic launch) the predecessor is still reducing: HBM would
+                    // idle, so pull the next tiles of this CTA into L2
+                    for (long long v = u + 1; v < u1 && v <= u + l2_ahead; ++v) {
+                        const int rb2 = static_cast<int>(v / n_kb), kb2 = static_cast<int>(v % n_kb);
+#pragma unroll
+                        for (int p = 0; p < PARTS; ++p) tma_prefetch_l2_2d(&tmW, kb2 * 64, op.a_row(b, rb2, p, sm));
+                    }
+                }
             }
-            // all of this CTA's weight loads are issued: with programmatic dependent launch the next kernel of the
-            // chain may now take the free half of the SM and fill its ring while this CTA drains and reduces
-            pdl_launch_dependents();
+            if (!triggered) {
+                if (flags & 2) pdl_wait();
+                pdl_launch_dependents();
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -298,16 +424,16 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- prologue + epilogue (128 threads)
+        if (!wide) op.pre_wait(b, sm, (flags & 1) != 0);   // constants only: L2 prefetch ahead of the dependency wait
         pdl_wait();   // activations come from the previous kernel
-        op.prologue(b, sm);
+        op.prologue(b, sm, wide);
         epi_barrier();
         if (!Op::kBulkX && threadIdx.x == 128) mbar_arrive(x_ready);
 
         const int quad = warp - 4;
         const int row = quad * 32 + lane;
         TcFinish st{-INFINITY, 0x7fffffff};
-        float* my_scratch = g_scratch + static_cast<long long>(b) * n_rb * TC_SLOTS * PARTS * 128;
-        int* my_tickets = g_tickets + static_cast<long long>(b) * n_rb;
+        unsigned long long* my_scratch = g_scratch + static_cast<long long>(b) * n_rb * TC_SLOTS * PARTS * 128;
         int acc = 0;
         uint32_t acc_phase = 0;
         long long u = u0;
@@ -315,6 +441,40 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
             const int rb = static_cast<int>(u / n_kb);
             const long long rb_begin = static_cast<long long>(rb) * n_kb, rb_end = rb_begin + n_kb;
             const long long seg_end = rb_end < u1 ? rb_end : u1;
+            // A K-partial segment is reduced through global slots in a fixed order (slot = contributor index).  Every
+            // partial travels as ONE 64-bit word {value, tag}, so neither fences nor tickets are needed: the contributor
+            // with the lowest index -- the CTA that ends on this row block, its neighbours did their part of it first --
+            // reduces, and clears the tags for the next launch.  While its own MMAs are still running it already
+            // collects whatever the others have published.
+            const bool partial = (u != rb_begin || seg_end != rb_end);
+            int slot = 0, n_contrib = 1;
+            unsigned long long* base64 = nullptr;
+            uint32_t have = 0;
+            float oth[PARTS][TC_SLOTS];
+            if (partial) {
+                int c_first = blockIdx.x;
+                while (c_first > 0 && U * c_first / G > rb_begin) --c_first;
+                int c_last = blockIdx.x;
+                while (c_last + 1 < G && U * (c_last + 1) / G < rb_end) ++c_last;
+                slot = blockIdx.x - c_first;
+                n_contrib = c_last - c_first + 1;
+                base64 = my_scratch + static_cast<long long>(rb) * TC_SLOTS * PARTS * 128;
+                if (slot == 0) {
+#pragma unroll
+                    for (int p = 0; p < PARTS; ++p) {
+                        unsigned long long w[TC_SLOTS];
+#pragma unroll
+                        for (int q = 1; q < TC_SLOTS; ++q)
+                            if (q < n_contrib) w[q] = ld_relaxed_u64(base64 + (q * PARTS + p) * 128 + row);
+#pragma unroll
+                        for (int q = 1; q < TC_SLOTS; ++q)
+                            if (q < n_contrib && (w[q] >> 32) != 0) {
+                                oth[p][q] = __uint_as_float(static_cast<uint32_t>(w[q]));
+                                have |= 1u << (p * TC_SLOTS + q);
+                            }
+                    }
+                }
+            }
             mbar_wait(&acc_full[acc], acc_phase, 27);
             tc_fence_after();
             float v[PARTS];
@@ -332,34 +492,39 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, float* __re
             if (acc == 0) acc_phase ^= 1;
 
             bool do_finish = true;
-            if (u != rb_begin || seg_end != rb_end) {
-                // partial K range: publish to this CTA's slot; the last contributor reduces all slots in order
-                int c_first = blockIdx.x;
-                while (c_first > 0 && U * c_first / G > rb_begin) --c_first;
-                int c_last = blockIdx.x;
-                while (c_last + 1 < G && U * (c_last + 1) / G < rb_end) ++c_last;
-                const int slot = blockIdx.x - c_first, n_contrib = c_last - c_first + 1;
-                float* base = my_scratch + static_cast<long long>(rb) * TC_SLOTS * PARTS * 128;
+            if (partial && slot != 0) {
 #pragma unroll
-                for (int p = 0; p < PARTS; ++p) __stcg(base + (slot * PARTS + p) * 128 + row, v[p]);
-                epi_barrier();   // cta-scope happens-before from every writer to the releasing thread
-                if (threadIdx.x == 128) {
-                    int t;
-                    asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(t) : "l"(my_tickets + rb) : "memory");
-                    misc[7] = (t == n_contrib - 1);
-                    if (t == n_contrib - 1) my_tickets[rb] = 0;
-                }
-                epi_barrier();
-                do_finish = misc[7] != 0;
-                if (do_finish) {
+                for (int p = 0; p < PARTS; ++p)
+                    st_relaxed_u64(base64 + (slot * PARTS + p) * 128 + row,
+                                   (1ull << 32) | static_cast<unsigned long long>(__float_as_uint(v[p])));
+                do_finish = false;
+            } else if (partial) {
 #pragma unroll
-                    for (int p = 0; p < PARTS; ++p) {
-                        float s = 0.0f;
-                        for (int q = 0; q < n_contrib; ++q) s += __ldcg(base + (q * PARTS + p) * 128 + row);
-                        v[p] = s;
+                for (int p = 0; p < PARTS; ++p)
+#pragma unroll
+                    for (int q = 1; q < TC_SLOTS; ++q) {
+                        if (q < n_contrib) {
+                            unsigned long long* addr = base64 + (q * PARTS + p) * 128 + row;
+                            if (!(have & (1u << (p * TC_SLOTS + q)))) {
+                                unsigned long long w = ld_relaxed_u64(addr);
+                                for (uint32_t spin = 0; (w >> 32) == 0; ++spin) {
+                                    if (spin > (1u << 26)) __trap();   // a contributor never published
+                                    w = ld_relaxed_u64(addr);
+                                }
+                                oth[p][q] = __uint_as_float(static_cast<uint32_t>(w));
+                            }
+                            st_relaxed_u64(addr, 0ull);   // consumed: the slot is free for the next launch
+                        }
                     }
+                // fixed order: own value (slot 0) first, then the slots ascending
+#pragma unroll
+                for (int p = 0; p < PARTS; ++p) {
+                    float s = 0.0f + v[p];
+#pragma unroll
+                    for (int q = 1; q < TC_SLOTS; ++q)
+                        if (q < n_contrib) s += oth[p][q];
+                    v[p] = s;
                 }
-                epi_barrier();   // misc[7] may be rewritten by the next segment
             }
             if (do_finish) op.finish(b, rb, row, v, st, sm);
             u = seg_end;
@@ -381,6 +546,7 @@ struct TcQkvOp {
     static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
     static constexpr int kParts = 1, kXParts = 1, kStages = 5;
+    static constexpr bool kHasRoute = false;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;
     const __nv_bfloat16* norm_w;
@@ -396,7 +562,9 @@ struct TcQkvOp {
     __device__ int x_elems() const { return K; }
     __device__ int num_row_blocks() const { return n_q + 2 * n_kv; }   // one 128-row block per head
     __device__ int a_row(int, int rb, int, const TcSmem&) const { return rb * 128; }
-    __device__ void prologue(int b, const TcSmem& sm) const {
+    __device__ void pre_wait(int, const TcSmem&, bool on) const { if (on) tc_prefetch_l2(norm_w, K * 2ll); }
+    __device__ void wide_partials(int, const TcSmem&) const {}
+    __device__ void prologue(int b, const TcSmem& sm, bool) const {
         const int t = threadIdx.x - 128;
         const int pos = cur_pos[b];
         sm.prep[t] = cos_sin[static_cast<long long>(pos) * 128 + t];
@@ -436,6 +604,7 @@ struct TcOProjOp {
     static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = true;
     static constexpr int kParts = 1, kXParts = 1, kStages = 5;
+    static constexpr bool kHasRoute = false;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* x;
     __nv_bfloat16* h;
@@ -444,7 +613,9 @@ struct TcOProjOp {
     __device__ int x_elems() const { return K; }
     __device__ int num_row_blocks() const { return (N + 127) / 128; }
     __device__ int a_row(int, int rb, int, const TcSmem&) const { return rb * 128; }
-    __device__ void prologue(int b, const TcSmem& sm) const { tc_bulk_x(x + static_cast<long long>(b) * K, sm.xs, K, sm.x_ready); }
+    __device__ void pre_wait(int, const TcSmem&, bool) const {}
+    __device__ void wide_partials(int, const TcSmem&) const {}
+    __device__ void prologue(int b, const TcSmem& sm, bool) const { tc_bulk_x(x + static_cast<long long>(b) * K, sm.xs, K, sm.x_ready); }
     __device__ void finish(int b, int rb, int row, const float (&v)[1], TcFinish&, const TcSmem&) const {
         const int r = rb * 128 + row;
         if (r < N) {
@@ -460,6 +631,7 @@ struct TcGateUpOp {
     static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
     static constexpr int kParts = 2, kXParts = 1, kStages = 3;
+    static constexpr bool kHasRoute = true;
     static constexpr bool kRowsNeedPrologue = true, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;
     const __nv_bfloat16* norm_w;
@@ -476,66 +648,45 @@ struct TcGateUpOp {
         const int nb = I / 128, k = rb / nb, jb = rb % nb;
         return sm.misc[k] * 2 * I + p * I + jb * 128;   // rows of the fused [E * 2I, H] weight
     }
-    __device__ void prologue(int b, const TcSmem& sm) const {
-        const int t = threadIdx.x - 128;
-        const __nv_bfloat16* hr = h + static_cast<long long>(b) * K;
+    __device__ void pre_wait(int, const TcSmem&, bool on) const {
+        if (!on) return;
+        tc_prefetch_l2(gate_w, 8ll * K * 2);
+        tc_prefetch_l2(norm_w, K * 2ll);
+    }
+    // wide form, part 1: all 256 threads of the CTA take a share of the router dot products (one round trip to L2)
+    __device__ void wide_partials(int b, const TcSmem& sm) const {
         float part[9];
-#pragma unroll
-        for (int e = 0; e < 9; ++e) part[e] = 0.0f;
-#pragma unroll 2
-        for (int i = t * 8; i < K; i += 128 * 8) {
-            const uint4 hv = *reinterpret_cast<const uint4*>(hr + i);
-            const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w + i));
-            uint4 ge[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ge[e] = __ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * K + i));
-            const uint32_t a[4] = {hv.x, hv.y, hv.z, hv.w}, gg[4] = {g.x, g.y, g.z, g.w};
-            float xw[8];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float lo = bf16_lo(a[q]), hi = bf16_hi(a[q]);
-                part[0] += lo * lo + hi * hi;
-                xw[2 * q] = lo * bf16_lo(gg[q]);
-                xw[2 * q + 1] = hi * bf16_hi(gg[q]);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const uint32_t w[4] = {ge[e].x, ge[e].y, ge[e].z, ge[e].w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) part[1 + e] += xw[2 * q] * bf16_lo(w[q]) + xw[2 * q + 1] * bf16_hi(w[q]);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 9; ++e) part[e] = warp_sum(part[e]);
-        const int w4 = (threadIdx.x >> 5) - 4;
+        tc_route_partials(h + static_cast<long long>(b) * K, norm_w, gate_w, K, threadIdx.x, TC_THREADS, part);
         if ((threadIdx.x & 31) == 0)
 #pragma unroll
-            for (int e = 0; e < 9; ++e) sm.prep[w4 * 9 + e] = part[e];
-        epi_barrier();
-        float tot[9];
+            for (int e = 0; e < 9; ++e) sm.prep[(threadIdx.x >> 5) * 9 + e] = part[e];
+    }
+    __device__ void prologue(int b, const TcSmem& sm, bool wide) const {
+        const int t = threadIdx.x - 128;
+        const __nv_bfloat16* hr = h + static_cast<long long>(b) * K;
+        TcRoute r;
+        if (wide) {
+            float tot[9];
 #pragma unroll
-        for (int e = 0; e < 9; ++e) tot[e] = sm.prep[e] + sm.prep[9 + e] + sm.prep[18 + e] + sm.prep[27 + e];
-        const float inv = rsqrtf(tot[0] / static_cast<float>(K) + eps);
-        float p[8], m = -INFINITY, sum = 0.0f;
+            for (int e = 0; e < 9; ++e) {
+                float s = 0.0f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { p[e] = tot[1 + e] * inv; m = fmaxf(m, p[e]); }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { p[e] = expf(p[e] - m); sum += p[e]; }
-        int e0 = 0;
-#pragma unroll
-        for (int e = 1; e < 8; ++e) if (p[e] > p[e0]) e0 = e;
-        int e1 = (e0 == 0) ? 1 : 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) if (e != e0 && p[e] > p[e1]) e1 = e;
+                for (int w = 0; w < TC_THREADS / 32; ++w) s += sm.prep[w * 9 + e];
+                tot[e] = s;
+            }
+            r = tc_route_finish(tot, K, eps);
+        } else {
+            r = tc_route(hr, norm_w, gate_w, K, eps, sm.prep);
+        }
+        const float inv = r.inv;
         if (t == 0) {
-            sm.misc[0] = e0;
-            sm.misc[1] = e1;
+            sm.misc[0] = r.e0;
+            sm.misc[1] = r.e1;
             if (blockIdx.x == 0) {
-                const float p0 = p[e0] / sum, p1 = p[e1] / sum, den = p0 + p1;
-                topk_ids[b * 2] = e0;
-                topk_ids[b * 2 + 1] = e1;
-                topk_w[b * 2] = p0 / den;
-                topk_w[b * 2 + 1] = p1 / den;
+                topk_ids[b * 2] = r.e0;
+                topk_ids[b * 2 + 1] = r.e1;
+                topk_w[b * 2] = r.w0;
+                topk_w[b * 2 + 1] = r.w1;
             }
         }
         for (int i = t * 8; i < K; i += 128 * 8) {
@@ -561,6 +712,7 @@ struct TcDownOp {
     static constexpr bool kXFromGlobal = true;
     static constexpr bool kBulkX = false;
     static constexpr int kParts = 2, kXParts = 2, kStages = 3;
+    static constexpr bool kHasRoute = false;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = true;
     const __nv_bfloat16* act;   // [B, 2, I]
     const int* topk_ids;
@@ -572,7 +724,9 @@ struct TcDownOp {
     __device__ const __nv_bfloat16* x_global(int b) const { return act + static_cast<long long>(b) * 2 * K; }
     __device__ int num_row_blocks() const { return (H + 127) / 128; }
     __device__ int a_row(int b, int rb, int p, const TcSmem&) const { return topk_ids[b * 2 + p] * H + rb * 128; }
-    __device__ void prologue(int b, const TcSmem& sm) const {
+    __device__ void pre_wait(int, const TcSmem&, bool) const {}
+    __device__ void wide_partials(int, const TcSmem&) const {}
+    __device__ void prologue(int b, const TcSmem& sm, bool) const {
         const int t = threadIdx.x - 128;
         if (t < 2) sm.prep[t] = topk_w[b * 2 + t];
     }
@@ -598,6 +752,7 @@ struct TcLmHeadOp {
     static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
     static constexpr int kParts = 1, kXParts = 1, kStages = 5;
+    static constexpr bool kHasRoute = false;
     static constexpr bool kRowsNeedPrologue = false, kRowsNeedUpstream = false;
     const __nv_bfloat16* h;
     long long h_stride;
@@ -610,7 +765,9 @@ struct TcLmHeadOp {
     __device__ int x_elems() const { return K; }
     __device__ int num_row_blocks() const { return (V + 127) / 128; }
     __device__ int a_row(int, int rb, int, const TcSmem&) const { return rb * 128; }
-    __device__ void prologue(int b, const TcSmem& sm) const {
+    __device__ void pre_wait(int, const TcSmem&, bool on) const { if (on) tc_prefetch_l2(norm_w, K * 2ll); }
+    __device__ void wide_partials(int, const TcSmem&) const {}
+    __device__ void prologue(int b, const TcSmem& sm, bool) const {
         tc_load_x_rmsnorm(h + static_cast<long long>(b) * h_stride, norm_w, sm.xs, K, eps, sm.scratch);
     }
     __device__ void finish(int b, int rb, int row, const float (&v)[1], TcFinish& st, const TcSmem&) const {
@@ -636,8 +793,7 @@ struct TcLmHeadOp {
 };
 
 struct TcWorkspace {
-    float* scratch;
-    int* tickets;
+    unsigned long long* scratch;   // [B][row blocks][TC_SLOTS][2][128] words {value, tag}; all tags zero between launches
 };
 
 template <class Op>
@@ -667,7 +823,11 @@ static int launch_tc(const Op& op, const void* W, long long w_rows, int K, int n
     if (g > num_sms()) g = num_sms();
     if (g < 1) g = 1;
     dim3 grid(static_cast<unsigned>(g), B);
-    cudaError_t e = launch_chain(kern, grid, dim3(TC_THREADS), smem_bytes, st, tm, op, ws.scratch, ws.tickets);
+    const int l2_ahead = option("tc_l2_ahead");   // tiles per CTA prefetched into L2 behind the ring
+    const int flags = (option("tc_prefetch_consts") ? 1 : 0) | (option("chain_wait") ? 2 : 0) |
+                      (option("tc_wide_route") ? 8 : 0) |
+                      (option("tc_trigger_lead") << 8);
+    cudaError_t e = launch_chain(kern, grid, dim3(TC_THREADS), smem_bytes, st, tm, op, ws.scratch, l2_ahead, flags);
     if (e != cudaSuccess) return check_cuda(e, name);
     return check_launch(name);
 }
@@ -678,15 +838,15 @@ static inline bool tc_shape_ok(long long K) { return K % 64 == 0 && K >= 64; }
 
 using namespace vita;
 
-// workspace: [tickets: B * max_rb ints][scratch: B * max_rb * SLOTS * 2 * 128 floats]; zero-initialised once.
+// workspace: [B * max_rb * SLOTS * 2 * 128 words of 8 bytes {partial sum, tag}]; zero-initialised once, the kernels
+// leave every tag cleared.
 extern "C" int64_t vita_decode_tc_workspace_bytes(int64_t B, int64_t max_row_blocks) {
-    return ((B * max_row_blocks * 4 + 255) / 256) * 256 + B * max_row_blocks * TC_SLOTS * 2 * 128 * 4;
+    return B * max_row_blocks * TC_SLOTS * 2 * 128 * 8;
 }
 
-static TcWorkspace split_ws(void* workspace, int64_t B, int64_t max_rb) {
+static TcWorkspace split_ws(void* workspace, int64_t, int64_t) {
     TcWorkspace ws;
-    ws.tickets = static_cast<int*>(workspace);
-    ws.scratch = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((B * max_rb * 4 + 255) / 256) * 256);
+    ws.scratch = static_cast<unsigned long long*>(workspace);
     return ws;
 }
 

@@ -380,3 +380,12 @@ class MegaDecode:
 
 def launch_count(reset: bool = False) -> int:
     return int(_lib.load().vita_launch_count(1 if reset else 0))
+
+
+def set_option(name: str, value: int) -> None:
+    """Library tunable ("pdl", "attn_early", "chain_wait", "tc_prefetch_consts", "tc_wide_route", "tc_l2_ahead", "tc_trigger_lead"); affects launches issued afterwards."""
+    _lib.call("vita_set_option", name.encode(), int(value))
+
+
+def get_option(name: str) -> int:
+    return int(_lib.load().vita_get_option(name.encode()))
