@@ -16,15 +16,15 @@ from vita_b200 import ops, weights as W          # noqa: E402
 from vita_b200.config import VitaConfig            # noqa: E402
 from vita_b200.model.mixtral import MixtralDecoder  # noqa: E402
 
-BASE = {"pdl": 1, "attn_early": 1, "chain_wait": 1, "tc_prefetch_consts": 1, "tc_l2_ahead": 0, "tc_trigger_lead": 0,
-        "tc_wide_route": 1}
+BASE = {"pdl": 1, "attn_early": 1, "attn_tagged": 1, "chain_wait": 1, "tc_prefetch_consts": 1, "tc_l2_ahead": 0,
+        "tc_trigger_lead": 0, "tc_wide_route": 1}
 CONFIGS = {
     # name: (library options on top of BASE, decoder attributes)
     "nopdl": ({"pdl": 0}, {}),
     "default": ({}, {}),
-    "narrow_route": ({"tc_wide_route": 0}, {}),
-    "no_attn_early": ({"attn_early": 0}, {}),
-    "no_const_prefetch": ({"tc_prefetch_consts": 0}, {}),
+    "attn_tickets": ({"attn_tagged": 0}, {}),
+    "splits12": ({}, {"decode_splits": 12}),
+    "splits8": ({}, {"decode_splits": 8}),
 }
 
 
@@ -56,6 +56,7 @@ def main():
             for k, v in attrs.items():
                 setattr(llm, k, v)
             llm._graph = None
+            llm.attn_ws.zero_()     # the two split-merge protocols use the same buffer differently
             llm.reset()
             llm.prefill(emb.clone(), slot=0)
             llm.decode_step(1, use_graph=True)   # capture + first token

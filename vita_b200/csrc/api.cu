@@ -51,6 +51,8 @@ static Option g_options[] = {
     {"tc_l2_ahead", "VITA_B200_TC_L2AHEAD", 0, {-1}},
     // paged decode attention: fetch the cached K/V rows ahead of the dependency wait (needs chain_wait)
     {"attn_early", "VITA_B200_ATTN_EARLY", 1, {-1}},
+    // paged decode attention: split partials as tagged 64-bit words collected by split 0 (no fence / ticket)
+    {"attn_tagged", "VITA_B200_ATTN_TAGGED", 1, {-1}},
     // chain kernels wait for their predecessor before they trigger their successor: when kernel N+1 starts, kernel
     // N-1 has completed (what attn_early relies on)
     {"chain_wait", "VITA_B200_CHAIN_WAIT", 1, {-1}},
@@ -79,6 +81,15 @@ int option(const char* name) {
 
 bool use_pdl() { return option("pdl") != 0; }
 
+#ifdef VITA_TRACE
+static unsigned long long* g_trace_base = nullptr;
+static long long g_trace_records = 0, g_trace_serial = 0;
+unsigned long long* trace_next_record() {
+    if (!g_trace_base || g_trace_records <= 0) return nullptr;
+    return g_trace_base + ((g_trace_serial++) % g_trace_records) * 32;
+}
+#endif
+
 }  // namespace vita
 
 extern "C" int vita_set_option(const char* name, int64_t value) {
@@ -94,6 +105,16 @@ extern "C" int vita_set_option(const char* name, int64_t value) {
 }
 
 extern "C" int64_t vita_get_option(const char* name) { return name ? vita::option(name) : 0; }
+
+#ifdef VITA_TRACE
+// instrumentation builds only: records = number of 32-word records in buf; restarts the launch serial
+extern "C" int vita_debug_trace(void* buf, int64_t records) {
+    vita::g_trace_base = static_cast<unsigned long long*>(buf);
+    vita::g_trace_records = records;
+    vita::g_trace_serial = 0;
+    return VITA_OK;
+}
+#endif
 
 namespace vita {
 

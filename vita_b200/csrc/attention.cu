@@ -290,14 +290,45 @@ __device__ __forceinline__ uint4 ld_early_v4(const void* ptr) {
     return r;
 }
 
+__device__ __forceinline__ unsigned long long attn_ld_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void attn_st_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// waits for a tagged word {value, tag != 0}, returns the value and frees the slot
+__device__ __forceinline__ float attn_take(unsigned long long* addr, unsigned long long w) {
+    for (uint32_t spin = 0; (w >> 32) == 0; ++spin) {
+        if (spin > (1u << 22)) __trap();   // a split never published
+        w = attn_ld_u64(addr);
+    }
+    attn_st_u64(addr, 0ull);
+    return __uint_as_float(static_cast<uint32_t>(w));
+}
+__device__ __forceinline__ float attn_rescale(float m_old, float m_new) {
+    return m_old == -INFINITY ? 0.0f : exp2f(m_old - m_new);
+}
+
+// TAGGED = false: splits are combined by the last CTA to take a ticket (fence + atomic + reload).
+// TAGGED = true : partials travel as 64-bit {value, tag} words in an all-to-all over the splits of a kv head: each CTA
+//                 owns a slice of the outputs and collects the other splits' words for it (no fence, no atomic, no
+//                 serial collector); lane groups are pre-merged with shuffles.
+template <bool TAGGED>
 __global__ void __launch_bounds__(128)
-decode_attn_kernel(const DecodeAttnParams p) {
+decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
     __shared__ float s_m[16][DEC_GROUP];
     __shared__ float s_l[16][DEC_GROUP];
-    __shared__ float s_o[16][DEC_GROUP][DEC_D];
+    __shared__ __align__(16) float s_o[TAGGED ? 4 : 16][DEC_GROUP][DEC_D];
+    __shared__ float s_ml[16][DEC_GROUP][2];
     __shared__ int s_last;
 
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+#ifdef VITA_TRACE
+    if (kvh != 0 || b != 0) trace = nullptr;
+    if (threadIdx.x == 0 && split == 0) { VITA_STAMP(1); VITA_STAMP_SET(0, 2ull); }
+#endif
     pdl_launch_dependents();
     if (!p.early) pdl_wait();
     // ---- before the dependency wait -------------------------------------------------------------------------------
@@ -341,6 +372,7 @@ decode_attn_kernel(const DecodeAttnParams p) {
         }
     }
     pdl_wait();   // q and the newest K/V row come from the QKV kernel
+    if (threadIdx.x == 0 && split == 0) VITA_STAMP(3);
 #pragma unroll
     for (int j = 0; j < NPRE; ++j) {
         const int key = k_begin + j * 16 + lg;
@@ -427,12 +459,129 @@ decode_attn_kernel(const DecodeAttnParams p) {
             consume(ka, kc, va, vc, key < k_end);
         }
     }
+    if constexpr (TAGGED) {
+        // ---- the 4 lane groups of each warp first (shuffles), then the 4 warps through shared memory
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+#pragma unroll
+            for (int h = 0; h < DEC_GROUP; ++h) {
+                const float mo = __shfl_xor_sync(0xffffffffu, m[h], off);
+                const float lo = __shfl_xor_sync(0xffffffffu, l[h], off);
+                const float mn = fmaxf(m[h], mo);
+                const float wa = attn_rescale(m[h], mn), wb = attn_rescale(mo, mn);
+                l[h] = l[h] * wa + lo * wb;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    acc[h][i] = acc[h][i] * wa + __shfl_xor_sync(0xffffffffu, acc[h][i], off) * wb;
+                m[h] = mn;
+            }
+        }
+        const int wid = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+            for (int h = 0; h < DEC_GROUP; ++h) {
+                if (sl == 0) { s_m[wid][h] = m[h]; s_l[wid][h] = l[h]; }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(&s_o[wid][h][d0 + i]) = make_float4(acc[h][i], acc[h][i + 1], acc[h][i + 2], acc[h][i + 3]);
+            }
+        }
+        __syncthreads();
+        const int d = threadIdx.x;  // one output dim per thread
+        float mm[DEC_GROUP], ll[DEC_GROUP], oo[DEC_GROUP];
+#pragma unroll
+        for (int h = 0; h < DEC_GROUP; ++h) {
+            mm[h] = fmaxf(fmaxf(s_m[0][h], s_m[1][h]), fmaxf(s_m[2][h], s_m[3][h]));
+            ll[h] = 0.0f; oo[h] = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float sc = attn_rescale(s_m[w][h], mm[h]);
+                ll[h] += sc * s_l[w][h];
+                oo[h] += sc * s_o[w][h][d];
+            }
+        }
+        __syncthreads();   // every thread is done reading s_m / s_l / s_o
+        // ---- all-to-all over the splits of this kv head: every CTA publishes its partials as tagged words and owns
+        // a 1/splits slice of the 4 x 128 outputs, for which it collects the other splits' words (one round trip,
+        // no fence, no ticket, no serial collector).  Each word has exactly one reader, which clears the tag.
+        const int S = p.splits;                    // 4, 8 or 16 (checked on the host)
+        const int P = DEC_GROUP * DEC_D / S;       // outputs owned by this CTA
+        unsigned long long* words = reinterpret_cast<unsigned long long*>(p.part_o);
+        const long long n_words_o = static_cast<long long>(gridDim.z) * p.n_kv * S * DEC_GROUP * DEC_D;
+        const long long grp = static_cast<long long>(b) * p.n_kv + kvh;
+        unsigned long long* o_w = words + grp * S * DEC_GROUP * DEC_D;                    // [publisher][head][dim]
+        unsigned long long* ml_w = words + n_words_o + grp * S * S * DEC_GROUP * 2;      // [publisher][reader][head][2]
+#ifdef VITA_TRACE
+        if (threadIdx.x == 0 && trace) trace[9 + (split & 15)] = global_timer_ns();
+#endif
+        // publish
+#pragma unroll
+        for (int h = 0; h < DEC_GROUP; ++h) {
+            s_o[0][h][d] = oo[h];   // own slice is read back from shared memory (s_o[0] is free again: all reads done)
+            if ((h * DEC_D + d) / P != split)
+                attn_st_u64(o_w + (split * DEC_GROUP + h) * DEC_D + d,
+                            (1ull << 32) | static_cast<unsigned long long>(__float_as_uint(oo[h])));
+        }
+        const int t = threadIdx.x;
+        const bool ml_thread = t < S * DEC_GROUP * 2;
+        const int peer = t >> 3, mh = (t & 7) >> 1, which = t & 1;
+        if (ml_thread) {
+            float val = 0.0f;
+#pragma unroll
+            for (int h = 0; h < DEC_GROUP; ++h)
+                if (h == mh) val = which ? ll[h] : mm[h];
+            if (peer == split) s_ml[split][mh][which] = val;
+            else attn_st_u64(ml_w + ((split * S + peer) * DEC_GROUP + mh) * 2 + which,
+                             (1ull << 32) | static_cast<unsigned long long>(__float_as_uint(val)));
+        }
+        // collect: all loads first, then poll what has not arrived yet
+        constexpr int MAXS = 16;
+        unsigned long long* ml_addr = ml_w + ((peer * S + split) * DEC_GROUP + mh) * 2 + which;
+        unsigned long long ml_word = 0;
+        if (ml_thread && peer != split) ml_word = attn_ld_u64(ml_addr);
+        const int flat = split * P + t;            // output handled by thread t < P
+        const int oh = flat / DEC_D, od = flat % DEC_D;
+        unsigned long long w[MAXS];
+        float os[MAXS];
+        if (t < P) {
+#pragma unroll
+            for (int sp = 0; sp < MAXS; ++sp)
+                if (sp < S && sp != split) w[sp] = attn_ld_u64(o_w + (sp * DEC_GROUP + oh) * DEC_D + od);
+        }
+        if (ml_thread && peer != split) s_ml[peer][mh][which] = attn_take(ml_addr, ml_word);
+        if (t < P) {
+#pragma unroll
+            for (int sp = 0; sp < MAXS; ++sp)
+                os[sp] = (sp < S && sp != split) ? attn_take(o_w + (sp * DEC_GROUP + oh) * DEC_D + od, w[sp]) : 0.0f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) VITA_STAMP(27);
+        if (t < P) {
+            float mt = -INFINITY;
+#pragma unroll
+            for (int sp = 0; sp < MAXS; ++sp)
+                if (sp < S) mt = fmaxf(mt, s_ml[sp][oh][0]);
+            float lt = 0.0f, ot = 0.0f;
+#pragma unroll
+            for (int sp = 0; sp < MAXS; ++sp) {
+                if (sp < S) {
+                    const float sc = attn_rescale(s_ml[sp][oh][0], mt);
+                    lt += sc * s_ml[sp][oh][1];
+                    ot += sc * (sp == split ? s_o[0][oh][od] : os[sp]);
+                }
+            }
+            p.out[(static_cast<long long>(b) * p.n_q + kvh * DEC_GROUP + oh) * DEC_D + od] =
+                __float2bfloat16(lt > 0.0f ? ot / lt : 0.0f);
+        }
+        if (threadIdx.x == 0) VITA_STAMP(8);
+        return;
+    }
     // merge the 16 lane groups of this CTA
 #pragma unroll
     for (int h = 0; h < DEC_GROUP; ++h) {
         if (sl == 0) { s_m[lg][h] = m[h]; s_l[lg][h] = l[h]; }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s_o[lg][h][d0 + i] = acc[h][i];
+        for (int i = 0; i < 16; ++i) s_o[TAGGED ? 0 : lg][h][d0 + i] = acc[h][i];
     }
     __syncthreads();
     const int d = threadIdx.x;  // one output dim per thread
@@ -448,12 +597,15 @@ decode_attn_kernel(const DecodeAttnParams p) {
             for (int gI = 0; gI < 16; ++gI) {
                 const float w = exp2f(s_m[gI][h] - mm);
                 ll += w * s_l[gI][h];
-                oo += w * s_o[gI][h][d];
+                oo += w * s_o[TAGGED ? 0 : gI][h][d];
             }
         }
         p.part_o[(pbase + h) * DEC_D + d] = oo;
         if (d == 0) { p.part_ml[(pbase + h) * 2] = mm; p.part_ml[(pbase + h) * 2 + 1] = ll; }
     }
+#ifdef VITA_TRACE
+    if (threadIdx.x == 0 && trace) trace[9 + (split & 15)] = global_timer_ns();
+#endif
     // last CTA of this (batch, kv head) merges the splits
     __threadfence();
     __syncthreads();
@@ -464,6 +616,7 @@ decode_attn_kernel(const DecodeAttnParams p) {
     }
     __syncthreads();
     if (!s_last) return;
+    if (threadIdx.x == 0) VITA_STAMP(25);
     __threadfence();
     const long long sbase = (static_cast<long long>(b) * p.n_kv + kvh) * p.splits * DEC_GROUP;
     constexpr int MAXS = 16;   // splits <= 16 (checked on the host); all loads of a head are issued before use
@@ -493,6 +646,7 @@ decode_attn_kernel(const DecodeAttnParams p) {
         p.out[(static_cast<long long>(b) * p.n_q + kvh * DEC_GROUP + h) * DEC_D + d] =
             __float2bfloat16(ll > 0.0f ? oo / ll : 0.0f);
     }
+    if (threadIdx.x == 0) VITA_STAMP(8);
 }
 
 }  // namespace vita
@@ -531,8 +685,9 @@ extern "C" int vita_attention_fwd(const void* q, const void* k, const void* v, v
 }
 
 extern "C" int64_t vita_decode_attention_workspace_bytes(int64_t B, int64_t n_kv_heads, int64_t splits) {
+    // 8-byte words {value, tag} for the split partials (the ticket variant uses the same buffer as plain floats)
     const int64_t n = B * n_kv_heads * splits * DEC_GROUP;
-    return n * DEC_D * 4 + n * 2 * 4 + B * n_kv_heads * 4 + 256;
+    return n * DEC_D * 8 + B * n_kv_heads * splits * splits * DEC_GROUP * 2 * 8 + ((B * n_kv_heads * 4 + 255) / 256) * 256 + 256;
 }
 
 extern "C" int vita_decode_attention(const void* q, const void* k_cache, const void* v_cache,
@@ -558,7 +713,11 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
     p.scale_log2 = scale * 1.4426950408889634f;
     p.early = option("attn_early");
     dim3 grid((unsigned)splits, (unsigned)n_kv_heads, (unsigned)B);
-    cudaError_t e = launch_chain(decode_attn_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p);
+    // the all-to-all protocol needs the split count to divide the 4 x 128 outputs into <= 128-wide slices
+    const bool tagged = option("attn_tagged") && (splits == 4 || splits == 8 || splits == 16);
+    cudaError_t e = tagged
+        ? launch_chain(decode_attn_kernel<true>, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p VITA_TRACE_ARG)
+        : launch_chain(decode_attn_kernel<false>, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p VITA_TRACE_ARG);
     if (e != cudaSuccess) return check_cuda(e, "decode_attn_kernel");
     return check_launch("decode_attn_kernel");
 }

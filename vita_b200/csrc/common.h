@@ -59,4 +59,16 @@ inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+
+// Optional timeline instrumentation (build with -DVITA_TRACE): the decode-chain kernels stamp %globaltimer at a few
+// points into one 32-word record per launch; scripts/decode_trace.py turns the records into a per-kernel timeline.
+#ifdef VITA_TRACE
+unsigned long long* trace_next_record();   // device pointer for the next launch, or nullptr when tracing is off
+#define VITA_TRACE_PARAM , unsigned long long* trace
+#define VITA_TRACE_ARG , trace_next_record()
+#else
+#define VITA_TRACE_PARAM
+#define VITA_TRACE_ARG
+#endif
+
 }  // namespace vita

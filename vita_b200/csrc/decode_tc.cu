@@ -228,7 +228,7 @@ template <class Op>
 #endif
 __global__ void __launch_bounds__(TC_THREADS, TC_MIN_BLOCKS)
 tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned long long* __restrict__ g_scratch,
-               const int l2_ahead, const int flags) {
+               const int l2_ahead, const int flags VITA_TRACE_PARAM) {
     constexpr int PARTS = Op::kParts, XPARTS = Op::kXParts, STAGES = Op::kStages;
     constexpr int STAGE_A = PARTS * TC_A_BYTES;
     constexpr int STAGE_X = XPARTS * TC_X_BYTES;
@@ -253,6 +253,11 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
 
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef VITA_TRACE
+    if (blockIdx.y != 0 || (blockIdx.x != 0 && blockIdx.x != gridDim.x - 1)) trace = nullptr;
+    if (trace && blockIdx.x != 0) trace += 16;         // last CTA: same events in words 17..24
+    if (threadIdx.x == 0) { VITA_STAMP(1); if (blockIdx.x == 0) VITA_STAMP_SET(0, static_cast<unsigned long long>(Op::kId)); }
+#endif
     const int K = op.K;
     const int n_kb = K >> 6;
     const int n_rb = op.num_row_blocks();
@@ -284,6 +289,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) VITA_STAMP(2);
 
     // router-carrying op, wide form: every thread of the CTA takes part in the router dot products before the roles
     // split up (the producer cannot start without the expert ids anyway)
@@ -335,6 +341,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
                 if (flags & 2) pdl_wait();
                 pdl_launch_dependents();
             }
+            VITA_STAMP(6);
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -354,6 +361,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
                 for (long long v = u; v < seg_end; ++v) {
                     mbar_wait(&full_bar[stage], phase, 24);
                     tc_fence_after();
+                    if (v == u0) VITA_STAMP(5);
 #pragma unroll
                     for (int p = 0; p < PARTS; ++p) {
                         const uint64_t da = umma_desc_k_sw128(sA_addr + stage * STAGE_A + p * TC_A_BYTES);
@@ -426,9 +434,11 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
         // ---------------------------------------------------------------- prologue + epilogue (128 threads)
         if (!wide) op.pre_wait(b, sm, (flags & 1) != 0);   // constants only: L2 prefetch ahead of the dependency wait
         pdl_wait();   // activations come from the previous kernel
+        if (threadIdx.x == 128) VITA_STAMP(3);
         op.prologue(b, sm, wide);
         epi_barrier();
         if (!Op::kBulkX && threadIdx.x == 128) mbar_arrive(x_ready);
+        if (threadIdx.x == 128) VITA_STAMP(4);
 
         const int quad = warp - 4;
         const int row = quad * 32 + lane;
@@ -477,6 +487,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
             }
             mbar_wait(&acc_full[acc], acc_phase, 27);
             tc_fence_after();
+            if (threadIdx.x == 128 && seg_end == u1) VITA_STAMP(7);
             float v[PARTS];
 #pragma unroll
             for (int p = 0; p < PARTS; ++p) {
@@ -530,6 +541,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
             u = seg_end;
         }
         op.finalize(b, st);
+        if (threadIdx.x == 128) VITA_STAMP(8);
     }
 
     tc_fence_before();
@@ -542,6 +554,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
 
 // ------------------------------------------------------------------------------------------------ ops
 struct TcQkvOp {
+    static constexpr int kId = 1;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
     static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
@@ -600,6 +613,7 @@ struct TcQkvOp {
 };
 
 struct TcOProjOp {
+    static constexpr int kId = 3;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
     static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = true;
@@ -627,6 +641,7 @@ struct TcOProjOp {
 };
 
 struct TcGateUpOp {
+    static constexpr int kId = 4;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
     static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
@@ -709,6 +724,7 @@ struct TcGateUpOp {
 };
 
 struct TcDownOp {
+    static constexpr int kId = 5;
     static constexpr bool kXFromGlobal = true;
     static constexpr bool kBulkX = false;
     static constexpr int kParts = 2, kXParts = 2, kStages = 3;
@@ -748,6 +764,7 @@ __device__ __forceinline__ unsigned long long tc_pack_argmax(float v, int idx) {
 }
 
 struct TcLmHeadOp {
+    static constexpr int kId = 6;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
     static constexpr bool kXFromGlobal = false;
     static constexpr bool kBulkX = false;
@@ -827,7 +844,7 @@ static int launch_tc(const Op& op, const void* W, long long w_rows, int K, int n
     const int flags = (option("tc_prefetch_consts") ? 1 : 0) | (option("chain_wait") ? 2 : 0) |
                       (option("tc_wide_route") ? 8 : 0) |
                       (option("tc_trigger_lead") << 8);
-    cudaError_t e = launch_chain(kern, grid, dim3(TC_THREADS), smem_bytes, st, tm, op, ws.scratch, l2_ahead, flags);
+    cudaError_t e = launch_chain(kern, grid, dim3(TC_THREADS), smem_bytes, st, tm, op, ws.scratch, l2_ahead, flags VITA_TRACE_ARG);
     if (e != cudaSuccess) return check_cuda(e, name);
     return check_launch(name);
 }

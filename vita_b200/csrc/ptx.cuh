@@ -180,4 +180,17 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
+#ifdef VITA_TRACE
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define VITA_STAMP(i) do { if (trace) trace[i] = global_timer_ns(); } while (0)
+#define VITA_STAMP_SET(i, v) do { if (trace) trace[i] = (v); } while (0)
+#else
+#define VITA_STAMP(i) do { } while (0)
+#define VITA_STAMP_SET(i, v) do { } while (0)
+#endif
+
 }  // namespace vita
