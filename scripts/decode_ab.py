@@ -17,14 +17,15 @@ from vita_b200.config import VitaConfig            # noqa: E402
 from vita_b200.model.mixtral import MixtralDecoder  # noqa: E402
 
 BASE = {"pdl": 1, "attn_early": 1, "attn_tagged": 1, "chain_wait": 1, "tc_prefetch_consts": 1, "tc_l2_ahead": 0,
-        "tc_trigger_lead": 0, "tc_wide_route": 1}
+        "tc_trigger_lead": 0, "tc_wide_route": 1, "smem_carveout_max": 0}
 CONFIGS = {
     # name: (library options on top of BASE, decoder attributes)
     "nopdl": ({"pdl": 0}, {}),
     "default": ({}, {}),
+    "carveout_default": ({"smem_carveout_max": 0}, {}),
+    "lead4": ({"tc_trigger_lead": 4}, {}),
+    "l2a4": ({"tc_l2_ahead": 4}, {}),
     "attn_tickets": ({"attn_tagged": 0}, {}),
-    "splits12": ({}, {"decode_splits": 12}),
-    "splits8": ({}, {"decode_splits": 8}),
 }
 
 

@@ -715,6 +715,15 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
     dim3 grid((unsigned)splits, (unsigned)n_kv_heads, (unsigned)B);
     // the all-to-all protocol needs the split count to divide the 4 x 128 outputs into <= 128-wide slices
     const bool tagged = option("attn_tagged") && (splits == 4 || splits == 8 || splits == 16);
+    {
+        static int carveout = -1;
+        const int want = option("smem_carveout_max") ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutDefault;
+        if (carveout != want) {
+            (void)cudaFuncSetAttribute(decode_attn_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, want);
+            (void)cudaFuncSetAttribute(decode_attn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, want);
+            carveout = want;
+        }
+    }
     cudaError_t e = tagged
         ? launch_chain(decode_attn_kernel<true>, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p VITA_TRACE_ARG)
         : launch_chain(decode_attn_kernel<false>, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p VITA_TRACE_ARG);

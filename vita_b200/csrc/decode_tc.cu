@@ -226,7 +226,13 @@ template <class Op>
 #ifndef TC_MIN_BLOCKS
 #define TC_MIN_BLOCKS 1
 #endif
-__global__ void __launch_bounds__(TC_THREADS, TC_MIN_BLOCKS)
+// Register cap: a kernel and its successor in a programmatic-launch chain share an SM (2 x 256 threads), and the
+// register file only holds both when their sum stays clearly below 256 per thread pair.
+#ifdef TC_NO_MAXNREG
+__global__ void __launch_bounds__(TC_THREADS, 1)
+#else
+__global__ void __maxnreg__(Op::kMaxRegs)
+#endif
 tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned long long* __restrict__ g_scratch,
                const int l2_ahead, const int flags VITA_TRACE_PARAM) {
     constexpr int PARTS = Op::kParts, XPARTS = Op::kXParts, STAGES = Op::kStages;
@@ -554,6 +560,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
 
 // ------------------------------------------------------------------------------------------------ ops
 struct TcQkvOp {
+    static constexpr int kMaxRegs = 128;
     static constexpr int kId = 1;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
     static constexpr bool kXFromGlobal = false;
@@ -613,6 +620,7 @@ struct TcQkvOp {
 };
 
 struct TcOProjOp {
+    static constexpr int kMaxRegs = 128;
     static constexpr int kId = 3;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
     static constexpr bool kXFromGlobal = false;
@@ -641,6 +649,7 @@ struct TcOProjOp {
 };
 
 struct TcGateUpOp {
+    static constexpr int kMaxRegs = 144;
     static constexpr int kId = 4;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
     static constexpr bool kXFromGlobal = false;
@@ -724,6 +733,7 @@ struct TcGateUpOp {
 };
 
 struct TcDownOp {
+    static constexpr int kMaxRegs = 96;
     static constexpr int kId = 5;
     static constexpr bool kXFromGlobal = true;
     static constexpr bool kBulkX = false;
@@ -764,6 +774,7 @@ __device__ __forceinline__ unsigned long long tc_pack_argmax(float v, int idx) {
 }
 
 struct TcLmHeadOp {
+    static constexpr int kMaxRegs = 128;
     static constexpr int kId = 6;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
     static constexpr bool kXFromGlobal = false;
@@ -831,6 +842,15 @@ static int launch_tc(const Op& op, const void* W, long long w_rows, int K, int n
         rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), name);
         if (rc) return rc;
         configured = smem_bytes;
+    }
+    // co-residency with the neighbours of a programmatic-launch chain needs the SM configured for maximum shared
+    // memory (the default carve-out only covers this kernel's own footprint)
+    static int carveout = -1;
+    const int want = option("smem_carveout_max") ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutDefault;
+    if (carveout != want) {
+        rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, want), name);
+        if (rc) return rc;
+        carveout = want;
     }
     // keep the number of contributors per row block <= TC_SLOTS: every CTA gets at least ceil(n_kb / 6) units
     const int n_kb = K / 64;
