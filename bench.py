@@ -421,8 +421,10 @@ def run_b200(args):
                         "encoders_tflops": encoder_flops(cfg) / (enc_ms / 1e3) / 1e12},
             "roofline": {"kernel": roof_kernel, "how": roof_note, "bound": "hbm", "achieved": gu_bytes / 1e9 / (gu_ms / 1e3),
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gu_bytes / 1e9 / (gu_ms / 1e3) / pk["hbm_gbs"],
-                         "traffic": None, "bytes_per_launch": gu_bytes, "us_per_launch": gu_ms * 1e3,
-                         "peak_source": pk["source"]},
+                         "traffic": ncu_traffic_bytes(roof_kernel), "bytes_per_launch": gu_bytes,
+                         "us_per_launch": gu_ms * 1e3, "peak_source": pk["source"],
+                         "traffic_source": "profiles/r01_prof_tc_gateup_full.md (ncu --set full, one launch, "
+                                           "dram__bytes_read.sum + dram__bytes_write.sum)"},
             "prefill_long": None if long_ms is None else {
                 "S": S_LONG, "ms": long_ms, "tflops": prefill_flops(S_LONG, cfg) / (long_ms / 1e3) / 1e12,
                 "tensor_frac": prefill_flops(S_LONG, cfg) / (long_ms / 1e3) / 1e12 / pk["tflops"],
@@ -445,6 +447,21 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic_bytes(kernel_name: str):
+    """DRAM bytes of one launch of the roofline kernel, from the committed ncu --set full summary (None if the active
+    decode path is not the profiled kernel or the summary is missing)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_prof_tc_gateup_full.md")
+    if "TcGateUpOp" not in kernel_name or not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for ln in open(path):
+        c = [x.strip() for x in ln.strip().strip("|").split("|")]
+        if len(c) >= 3 and c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and c[2] in unit:
+            tot += float(c[1]) * unit[c[2]]
+    return tot or None
 
 
 def main():
