@@ -144,6 +144,16 @@ int vita_vit_pixel_shuffle(const void* h, void* out, int64_t n_img, int64_t grid
                            void* stream);
 
 /* ---- Whale audio front end -------------------------------------------------------------------------------- */
+/* Kaldi log-mel filterbank = torchaudio.compliance.kaldi.fbank as the reference calls it in
+ * audioEncoderProcessor.process (whale/init_model.py:48-56: 25 ms povey window, 10 ms shift, snip_edges, DC removal,
+ * pre-emphasis 0.97 with the first sample replicated, 512-point power spectrum, log floored at FLT_EPSILON; dither 0).
+ * wave: [n_samples] fp32, already multiplied by 2^15 (init_model.py:47); window: [frame_len]; mel_weights_t:
+ * [256, n_mel] (fft bin major) triangular filters; mel_span: [n_mel, 2] = [first, last) non-zero bin of each filter;
+ * out: [n_frames, n_mel] fp32 with n_frames = 1 + (n_samples - frame_len) / frame_shift (0 frames: no launch).
+ * Output feeds vita_whale_conv1 directly. */
+int vita_fbank(const float* wave, int64_t n_samples, const float* window, const float* mel_weights_t,
+               const int32_t* mel_span, float* out, int64_t frame_len, int64_t frame_shift, int64_t n_mel,
+               float preemph, void* stream);
 /* GlobalCMVN (cmvn.py:21-32, mean/istd may be NULL) + Conv2d(1,C,3,2) + ReLU (subsampling.py:28-29); feat fp32
  * [B,T,F]; out channels-last [B,T1,F1,C]. */
 int vita_whale_conv1(const float* feat, const float* mean, const float* istd, const void* w, const void* bias,

@@ -24,7 +24,10 @@ class AudioEncoder:
         self.llm_hidden = llm_hidden
         self.device = torch.device(device)
         self.dtype = BF16
-        self.audio_processor = None  # waveform -> fbank is CPU preprocessing (set by the builder when available)
+        # `.audio_processor.process(path) -> (fbank [T, 80], n_llm_tokens)` as the demo uses it
+        # (video_audio_demo.py:183-187); the filterbank itself runs on the GPU (csrc/fbank.cu)
+        from ..audio_frontend import AudioProcessor
+        self.audio_processor = AudioProcessor(device)
 
     def to(self, *args, **kwargs):  # the demo calls audio_encoder.to(dtype=torch.float16) (video_audio_demo.py:176)
         return self

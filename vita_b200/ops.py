@@ -235,6 +235,20 @@ def vit_pixel_shuffle(h, out, n_img, grid, C, scale):
 
 
 # ------------------------------------------------------------------------------------------------ Whale glue
+def fbank(wave, window, mel_weights_t, mel_span, frame_len: int, frame_shift: int, preemph: float) -> torch.Tensor:
+    """wave: [n] fp32 on the device, already scaled by 2**15.  Returns [n_frames, n_mel] fp32 (kaldi log-mel)."""
+    _chk(wave, torch.float32, "wave"); _chk(window, torch.float32, "window")
+    _chk(mel_weights_t, torch.float32, "mel_weights_t"); _chk(mel_span, torch.int32, "mel_span")
+    n = wave.numel()
+    n_mel = mel_weights_t.shape[1]
+    n_frames = 0 if n < frame_len else 1 + (n - frame_len) // frame_shift
+    out = torch.empty(n_frames, n_mel, dtype=torch.float32, device=wave.device)
+    if n_frames:
+        _lib.call("vita_fbank", _p(wave), n, _p(window), _p(mel_weights_t), _p(mel_span), _p(out), frame_len,
+                  frame_shift, n_mel, float(preemph), _stream())
+    return out
+
+
 def whale_conv1(feat, mean, istd, w, bias, out):
     _chk(feat, torch.float32, "feat"); _chk(w, BF16, "w"); _chk(bias, BF16, "bias"); _chk(out, BF16, "out")
     B, T, F = feat.shape
