@@ -143,6 +143,22 @@ int vita_vit_assemble(const void* patches, const void* cls, const void* pos, voi
 int vita_vit_pixel_shuffle(const void* h, void* out, int64_t n_img, int64_t grid, int64_t C, float scale,
                            void* stream);
 
+/* ---- image front end ---------------------------------------------------------------------------------------- */
+/* One separable pass of Pillow's 8-bit resampler (what `image.resize(...)` runs inside the reference's
+ * dynamic_preprocess, data_utils_video_audio_neg_patch.py:1239,1253; Pillow src/libImaging/Resample.c):
+ *   out[o, p, c] = clip8((2^21 + sum_k in[bounds[o][0] + k, p, c] * kk[o][k]) >> 22),  k < bounds[o][1]
+ * along `axis` (1 = horizontal pass: [H, W, C] -> [H, out_size, C]; 0 = vertical pass: [H, W, C] -> [out_size, W, C])
+ * of an interleaved uint8 image.  kk [out_size, ksize] int32 fixed-point coefficients and bounds [out_size, 2] come
+ * from the host (vita_b200/image_frontend.py::resample_tables = Resample.c precompute_coeffs + normalize_coeffs_8bpc).
+ * Pillow's order for a 2-D resize: horizontal pass first, then vertical. */
+int vita_image_resample_u8(const uint8_t* in, uint8_t* out, int64_t H, int64_t W, int64_t C, int axis,
+                           int64_t out_size, const int32_t* kk, const int32_t* bounds, int64_t ksize, void* stream);
+/* Tiling (dynamic_preprocess :1241-1250, row-major T x T tiles of a [gj*T, gi*T, 3] image) fused with
+ * CLIPImageProcessor's rescale + normalise through a [3, 256] bf16 table (mm_utils.py:30-43):
+ * out[tile0 + ty*gi + tx][c][y][x] = lut[c][img[ty*T + y][tx*T + x][c]];  out is [N, 3, T, T] bf16. */
+int vita_image_tiles_lut(const uint8_t* img, const void* lut, void* out, int64_t gi, int64_t gj, int64_t T,
+                         int64_t tile0, void* stream);
+
 /* ---- Whale audio front end -------------------------------------------------------------------------------- */
 /* Kaldi log-mel filterbank = torchaudio.compliance.kaldi.fbank as the reference calls it in
  * audioEncoderProcessor.process (whale/init_model.py:48-56: 25 ms povey window, 10 ms shift, snip_edges, DC removal,

@@ -47,6 +47,8 @@ SIGNATURES = {
     "vita_vit_im2col": (c_int, [P, P, I64, I64, I64, I64, I64, P]),
     "vita_vit_assemble": (c_int, [P, P, P, P, I64, I64, I64, P]),
     "vita_vit_pixel_shuffle": (c_int, [P, P, I64, I64, I64, c_float, P]),
+    "vita_image_resample_u8": (c_int, [P, P, I64, I64, I64, c_int, I64, P, P, I64, P]),
+    "vita_image_tiles_lut": (c_int, [P, P, P, I64, I64, I64, I64, P]),
     "vita_fbank": (c_int, [P, I64, P, P, P, P, I64, I64, I64, c_float, P]),
     "vita_whale_conv1": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "vita_whale_im2col2": (c_int, [P, P, I64, I64, I64, I64, P]),

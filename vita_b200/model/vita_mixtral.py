@@ -139,11 +139,27 @@ class VITAMixtralForCausalLM:
     def resize_token_embeddings(self, n: int):
         assert n == self.config.llm.vocab_size, "vita_b200 does not resize packed embeddings"
 
+    @property
+    def image_processor(self):
+        if getattr(self, "_image_processor", None) is None:
+            from ..image_frontend import ImageProcessor
+            self._image_processor = ImageProcessor(self.device)
+        return self._image_processor
+
     def process_images(self, images, model_cfg=None):
-        """CPU preprocessing (vita_mixtral.py:397-415) is left to the caller's CLIPImageProcessor; tensors pass through."""
-        if isinstance(images, (list, tuple)):
+        """vita_mixtral.py:397-415 / mm_utils.py:30-43: the tiles `dynamic_preprocess` cut on the host (448 x 448 PIL
+        images or uint8 arrays) -> [N, 3, 448, 448]; rescale + normalise run on the GPU (csrc/image.cu), bit-equal to
+        CLIPImageProcessor followed by the demo's cast to the model dtype.  Tensors pass through unchanged."""
+        if torch.is_tensor(images):
+            return images
+        if isinstance(images, (list, tuple)) and len(images) and torch.is_tensor(images[0]) and images[0].is_floating_point():
             return torch.stack([torch.as_tensor(im) for im in images])
-        return images
+        return self.image_processor.process_tiles(list(images))
+
+    def preprocess_image(self, image, min_num: int = 1, max_num: int = 12, use_thumbnail: bool = True):
+        """dynamic_preprocess + process_images (video_audio_demo.py:214-221) as one device-side pipeline: a decoded
+        RGB image (PIL / [H, W, 3] uint8) -> (pixel_values [N, 3, 448, 448] bf16, N)."""
+        return self.image_processor.preprocess(image, min_num, max_num, use_thumbnail)
 
     # -- encoders --------------------------------------------------------------------------------------------
     @torch.no_grad()

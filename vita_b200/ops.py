@@ -234,6 +234,22 @@ def vit_pixel_shuffle(h, out, n_img, grid, C, scale):
     _lib.call("vita_vit_pixel_shuffle", _p(h), _p(out), n_img, grid, C, float(scale), _stream())
 
 
+# ------------------------------------------------------------------------------------------------ image front end
+def image_resample_u8(img: torch.Tensor, axis: int, out_size: int, kk: torch.Tensor, bounds: torch.Tensor) -> torch.Tensor:
+    """One Pillow-exact bicubic pass over `axis` of an interleaved [H, W, C] uint8 image."""
+    _chk(img, torch.uint8, "img"); _chk(kk, torch.int32, "kk"); _chk(bounds, torch.int32, "bounds")
+    H, W, C = img.shape
+    out = torch.empty((H, out_size, C) if axis == 1 else (out_size, W, C), dtype=torch.uint8, device=img.device)
+    _lib.call("vita_image_resample_u8", _p(img), _p(out), H, W, C, axis, out_size, _p(kk), _p(bounds), kk.shape[1],
+              _stream())
+    return out
+
+
+def image_tiles_lut(img: torch.Tensor, lut: torch.Tensor, out: torch.Tensor, gi: int, gj: int, T: int, tile0: int) -> None:
+    _chk(img, torch.uint8, "img"); _chk(lut, BF16, "lut"); _chk(out, BF16, "out")
+    _lib.call("vita_image_tiles_lut", _p(img), _p(lut), _p(out), gi, gj, T, tile0, _stream())
+
+
 # ------------------------------------------------------------------------------------------------ Whale glue
 def fbank(wave, window, mel_weights_t, mel_span, frame_len: int, frame_shift: int, preemph: float) -> torch.Tensor:
     """wave: [n] fp32 on the device, already scaled by 2**15.  Returns [n_frames, n_mel] fp32 (kaldi log-mel)."""
