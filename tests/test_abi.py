@@ -54,3 +54,17 @@ def test_product_never_imports_the_oracle():
     for p in (ROOT / "vita_b200").rglob("*.py"):
         src = p.read_text()
         assert "import oracle" not in src and "from oracle" not in src, p
+
+
+def test_library_options_round_trip():
+    """vita_set_option / vita_get_option: environment-independent defaults, overrides, unknown names (no GPU needed)."""
+    from vita_b200 import _lib, ops
+    for name in ("pdl", "attn_early", "attn_tagged", "chain_wait", "tc_prefetch_consts", "tc_wide_route"):
+        assert ops.get_option(name) in (0, 1)
+    before = ops.get_option("tc_l2_ahead")
+    ops.set_option("tc_l2_ahead", 5)
+    assert ops.get_option("tc_l2_ahead") == 5
+    ops.set_option("tc_l2_ahead", before)
+    import pytest
+    with pytest.raises(_lib.VitaB200Error):
+        ops.set_option("no_such_option", 1)

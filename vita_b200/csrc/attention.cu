@@ -714,7 +714,10 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
     p.early = option("attn_early");
     dim3 grid((unsigned)splits, (unsigned)n_kv_heads, (unsigned)B);
     // the all-to-all protocol needs the split count to divide the 4 x 128 outputs into <= 128-wide slices
-    const bool tagged = option("attn_tagged") && (splits == 4 || splits == 8 || splits == 16);
+    // ... and every CTA of a kv head polls its peers, so all of them have to be resident at once: keep that to grids
+    // that fit the machine (two 128-thread CTAs per SM), larger batches take the ticket variant
+    const bool tagged = option("attn_tagged") && (splits == 4 || splits == 8 || splits == 16) &&
+                        splits * n_kv_heads * B <= 2ll * (num_sms() > 0 ? num_sms() : 148);
     {
         static int carveout = -1;
         const int want = option("smem_carveout_max") ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutDefault;
