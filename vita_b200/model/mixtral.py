@@ -262,10 +262,6 @@ class MixtralDecoder:
         l2pf = self.l2_prefetch
         main = torch.cuda.current_stream()
         for li, lw in enumerate(w["layers"]):
-            if l2pf:
-                # side stream: once the previous layer's down projection is done streaming... the o-proj weights can
-                # come into L2 while qkv + attention (both far from saturating HBM) run
-                pass
             if tc:
                 ops.decode_tc_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
                                        self.d_q[:B], cache.k[li], cache.v[li], ws, nq, nkv, D, cache.page_size,
