@@ -128,3 +128,64 @@ def normalize_tiles(tiles_u8: np.ndarray) -> np.ndarray:
     std = np.asarray(STD, dtype=np.float32)
     x = (x - mean) / std
     return np.ascontiguousarray(x.transpose(0, 3, 1, 2)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ video frames
+def expand2square(img: np.ndarray, background) -> np.ndarray:
+    """mm_utils.py:16-28 / video_audio_demo.py:86-97: pad the short side with the background colour, image centred."""
+    h, w, _ = img.shape
+    if w == h:
+        return img
+    s = max(w, h)
+    out = np.empty((s, s, 3), dtype=np.uint8)
+    out[...] = np.asarray(background, dtype=np.uint8)
+    if w > h:
+        out[(w - h) // 2:(w - h) // 2 + h, :] = img
+    else:
+        out[:, (h - w) // 2:(h - w) // 2 + w] = img
+    return out
+
+
+def clip_resize_crop(img: np.ndarray, size: int = IMAGE_SIZE) -> np.ndarray:
+    """CLIPImageProcessor of transformers 4.41 (the reference's pin; PIL backend): shortest edge -> `size` with the long
+    edge int(size * long / short), PIL bicubic, then centre crop size x size (top = (h - size) // 2)."""
+    h, w, _ = img.shape
+    short, long = (w, h) if w <= h else (h, w)
+    new_long = int(size * long / short)
+    nh, nw = (new_long, size) if w <= h else (size, new_long)
+    r = resize_bicubic(img, nw, nh)
+    top, left = (nh - size) // 2, (nw - size) // 2
+    return np.ascontiguousarray(r[top:top + size, left:left + size])
+
+
+def preprocess_frames(frames, pad: bool = True) -> np.ndarray:
+    """video_audio_demo.py:83-110: (expand2square with int(mean * 255)) -> CLIP preprocess: [T, 3, 448, 448] float32."""
+    bg = tuple(int(x * 255) for x in MEAN)
+    tiles = [clip_resize_crop(expand2square(f, bg) if pad else f) for f in frames]
+    return normalize_tiles(np.stack(tiles))
+
+
+def sample_frame_positions(n_frames: int, fps: float, max_frames: int, min_frames: int = 4, video_framerate: int = 1,
+                           s=None, e=None):
+    """Index arithmetic of `_get_rawvideo_dec` (video_audio_demo.py:43-81): which decoded frames are kept."""
+    if s is None:
+        start_time, end_time = None, None
+    else:
+        start_time, end_time = int(s), int(e)
+        start_time = start_time if start_time >= 0.0 else 0.0
+        end_time = end_time if end_time >= 0.0 else 0.0
+        if start_time > end_time:
+            start_time, end_time = end_time, start_time
+        elif start_time == end_time:
+            end_time = start_time + 1
+    f_start = 0 if start_time is None else int(start_time * fps)
+    f_end = int(min(1000000000 if end_time is None else end_time * fps, n_frames - 1))
+    if f_end - f_start + 1 <= 0:
+        return []
+    t_stride = int(round(float(fps) / int(video_framerate)))
+    all_pos = list(range(f_start, f_end + 1, t_stride))
+    if len(all_pos) > max_frames:
+        return [all_pos[i] for i in np.linspace(0, len(all_pos) - 1, num=max_frames, dtype=int)]
+    if len(all_pos) < min_frames:
+        return [all_pos[i] for i in np.linspace(0, len(all_pos) - 1, num=min_frames, dtype=int)]
+    return all_pos

@@ -59,6 +59,32 @@ def main():
         out[name + "_n_tiles"] = np.array(n[0])
         out[name + "_tile0_crop"] = t[0, :32, :32].copy()
         print(name, img.shape, "->", t.shape, sha(t)[:12], sha(pv.view(torch.int16).numpy())[:12])
+    # video frames (video_audio_demo.py:83-110): expand2square with int(mean * 255) + CLIP preprocess.  The reference
+    # pins transformers 4.41.1, whose CLIPImageProcessor resizes through PIL; in the installed 5.x that behaviour is
+    # CLIPImageProcessorPil (the default class moved to a torchvision backend that is not bit-compatible).
+    from transformers.models.clip import CLIPImageProcessorPil
+    ipp = CLIPImageProcessorPil(crop_size=448, do_center_crop=True, do_normalize=True, do_resize=True,
+                                image_mean=[0.485, 0.456, 0.406], image_std=[0.229, 0.224, 0.225], resample=3, size=448)
+
+    def expand2square(pil_img, background_color):          # as the demo defines it inline
+        width, height = pil_img.size
+        if width == height:
+            return pil_img
+        side = max(width, height)
+        result = Image.new(pil_img.mode, (side, side), background_color)
+        result.paste(pil_img, (0, (width - height) // 2) if width > height else ((height - width) // 2, 0))
+        return result
+
+    frames = {"landscape": (180, 320, 6), "portrait": (321, 179, 7), "sq": (200, 200, 8)}
+    bg = tuple(int(x * 255) for x in ipp.image_mean)
+    for name, (h, w, k) in frames.items():
+        img = pattern(h, w, k)
+        out["frame_" + name] = img
+        for pad in (True, False):
+            pil = Image.fromarray(img)
+            pv = ipp.preprocess(expand2square(pil, bg) if pad else pil, return_tensors="pt")["pixel_values"].to(torch.bfloat16)
+            out[f"frame_{name}_pad{int(pad)}_pixels_bf16_sha256"] = np.array(sha(pv.view(torch.int16).numpy()))
+            print("frame", name, "pad" if pad else "nopad", tuple(pv.shape), sha(pv.view(torch.int16).numpy())[:12])
     # every uint8 value through the processor: the 3 x 256 table the GPU path indexes
     ramp = np.tile(np.arange(256, dtype=np.uint8)[None, :, None], (448, 2, 3))[:, :448]
     pv = ip.preprocess([Image.fromarray(ramp)], return_tensors="pt")["pixel_values"][0].to(torch.bfloat16)

@@ -70,3 +70,19 @@ def test_process_images_and_model_entry_points(proc):
     assert torch.equal(px, px2) and n == tiles.shape[0]
     with pytest.raises(ValueError):
         model.process_images([img], model.config)          # not a 448 x 448 tile
+
+
+@pytest.mark.parametrize("name", ["landscape", "portrait", "sq"])
+@pytest.mark.parametrize("pad", [True, False])
+def test_video_frames_reproduce_reference_bits(proc, name, pad):
+    """video_audio_demo.py:83-110: expand2square + CLIP preprocess (transformers 4.41 = PIL backend) per frame."""
+    px = proc.preprocess_frames([GOLD["frame_" + name]], pad=pad)
+    assert px.is_cuda and tuple(px.shape) == (1, 3, 448, 448)
+    assert sha(px.cpu().view(torch.int16).numpy()) == str(GOLD[f"frame_{name}_pad{int(pad)}_pixels_bf16_sha256"])
+
+
+def test_video_frame_batch(proc):
+    frames = [GOLD["frame_landscape"], GOLD["frame_portrait"], GOLD["frame_sq"], GOLD["frame_landscape"]]
+    px = proc.preprocess_frames(frames)
+    want = torch.from_numpy(O.preprocess_frames(frames)).to(torch.bfloat16)
+    assert torch.equal(px.cpu(), want)

@@ -78,13 +78,52 @@ def normalize_lut() -> torch.Tensor:
     return torch.from_numpy(((v[None, :] - mean) / std).astype(np.float32)).to(torch.bfloat16)
 
 
-class ImageProcessor:
-    """`preprocess(image)` = dynamic_preprocess + process_images of the reference in one device-side pipeline."""
+def sample_frame_positions(n_frames: int, fps: float, max_frames: int, min_frames: int = 4, video_framerate: int = 1,
+                           s=None, e=None):
+    """Which decoded frames a video contributes (`_get_rawvideo_dec`, video_audio_demo.py:43-81): one frame per
+    1 / video_framerate seconds inside [s, e], thinned to `max_frames` / repeated up to `min_frames` with
+    `np.linspace(..., dtype=int)` exactly as the reference does.  Decoding itself (decord) stays on the host."""
+    if s is None:
+        start_time = end_time = None
+    else:
+        start_time, end_time = max(int(s), 0), max(int(e), 0)
+        if start_time > end_time:
+            start_time, end_time = end_time, start_time
+        elif start_time == end_time:
+            end_time = start_time + 1
+    f_start = 0 if start_time is None else int(start_time * fps)
+    f_end = int(min(1000000000 if end_time is None else end_time * fps, n_frames - 1))
+    if f_end < f_start:
+        return []
+    stride = int(round(float(fps) / int(video_framerate)))
+    all_pos = list(range(f_start, f_end + 1, stride))
+    want = max_frames if len(all_pos) > max_frames else (min_frames if len(all_pos) < min_frames else None)
+    if want is None:
+        return all_pos
+    return [all_pos[i] for i in np.linspace(0, len(all_pos) - 1, num=want, dtype=int)]
 
-    def __init__(self, device="cuda", image_size: int = IMAGE_SIZE):
+
+class _CudaBackend:
+    """The two byte kernels of csrc/image.cu.  (Tests substitute a numpy stand-in to check the host-side geometry on
+    machines without a GPU; the product never does.)"""
+
+    def resample(self, img, axis, out_size, kk, bounds):
+        return ops.image_resample_u8(img, axis, out_size, kk, bounds)
+
+    def tiles_lut(self, img, lut, out, gi, gj, T, tile0):
+        ops.image_tiles_lut(img, lut, out, gi, gj, T, tile0)
+
+
+class ImageProcessor:
+    """`preprocess(image)` = dynamic_preprocess + process_images of the reference in one device-side pipeline;
+    `preprocess_frames(frames)` = the per-frame CLIP preprocessing of the video path."""
+
+    def __init__(self, device="cuda", image_size: int = IMAGE_SIZE, backend=None):
         self.device = torch.device(device)
         self.image_size = image_size
+        self.backend = backend or _CudaBackend()
         self.lut = normalize_lut().to(self.device)
+        self.background = torch.tensor([int(x * 255) for x in IMAGE_MEAN], dtype=torch.uint8, device=self.device)
         self._tables = {}
 
     def _dev_tables(self, in_size: int, out_size: int):
@@ -102,10 +141,10 @@ class ImageProcessor:
         out = img
         if width != w:
             kk, bounds = self._dev_tables(w, width)
-            out = ops.image_resample_u8(out, 1, width, kk, bounds)
+            out = self.backend.resample(out, 1, width, kk, bounds)
         if height != h:
             kk, bounds = self._dev_tables(h, height)
-            out = ops.image_resample_u8(out, 0, height, kk, bounds)
+            out = self.backend.resample(out, 0, height, kk, bounds)
         return out
 
     def to_device_u8(self, image) -> torch.Tensor:
@@ -134,9 +173,9 @@ class ImageProcessor:
         T = self.image_size
         n = gi * gj + (1 if thumb is not None else 0)
         out = torch.empty(n, 3, T, T, dtype=torch.bfloat16, device=self.device)
-        ops.image_tiles_lut(big, self.lut, out, gi, gj, T, 0)
+        self.backend.tiles_lut(big, self.lut, out, gi, gj, T, 0)
         if thumb is not None:
-            ops.image_tiles_lut(thumb, self.lut, out, 1, 1, T, gi * gj)
+            self.backend.tiles_lut(thumb, self.lut, out, 1, 1, T, gi * gj)
         return out, n
 
     def process_tiles(self, tiles) -> torch.Tensor:
@@ -147,5 +186,44 @@ class ImageProcessor:
             u8 = self.to_device_u8(t)
             if u8.shape[0] != T or u8.shape[1] != T:      # CLIPImageProcessor would resize + centre-crop: not the tiled path
                 raise ValueError("process_tiles expects 448 x 448 tiles (use preprocess() for whole images)")
-            ops.image_tiles_lut(u8, self.lut, out, 1, 1, T, i)
+            self.backend.tiles_lut(u8, self.lut, out, 1, 1, T, i)
+        return out
+
+    # -- video frames (video_audio_demo.py:83-110) -----------------------------------------------------------------
+    def expand2square(self, img: torch.Tensor) -> torch.Tensor:
+        """Pad the short side with int(mean * 255), image centred (mm_utils.py:16-28).  Byte copies only."""
+        h, w, _ = img.shape
+        if w == h:
+            return img
+        s = max(w, h)
+        out = self.background.expand(s, s, 3).contiguous()
+        if w > h:
+            out[(w - h) // 2:(w - h) // 2 + h, :] = img
+        else:
+            out[:, (h - w) // 2:(h - w) // 2 + w] = img
+        return out
+
+    def clip_resize_crop(self, img: torch.Tensor) -> torch.Tensor:
+        """CLIPImageProcessor geometry (transformers 4.41, PIL backend): shortest edge -> 448 with the long edge
+        int(448 * long / short), bicubic, centre crop 448 x 448."""
+        T = self.image_size
+        h, w, _ = img.shape
+        short, long = (w, h) if w <= h else (h, w)
+        new_long = int(T * long / short)
+        nh, nw = (new_long, T) if w <= h else (T, new_long)
+        r = self.resize(img, nw, nh)
+        top, left = (nh - T) // 2, (nw - T) // 2
+        return r[top:top + T, left:left + T].contiguous()
+
+    def preprocess_frames(self, frames, pad: bool = True) -> torch.Tensor:
+        """Decoded video frames (sequence of [H, W, 3] uint8 / PIL images, or one [T, H, W, 3] array) ->
+        [T, 3, 448, 448] bf16: expand2square (image_aspect_ratio == "pad") + CLIP resize / crop / rescale / normalise."""
+        T = self.image_size
+        frames = list(frames)
+        out = torch.empty(len(frames), 3, T, T, dtype=torch.bfloat16, device=self.device)
+        for i, f in enumerate(frames):
+            u8 = self.to_device_u8(f)
+            if pad:
+                u8 = self.expand2square(u8)
+            self.backend.tiles_lut(self.clip_resize_crop(u8), self.lut, out, 1, 1, T, i)
         return out
