@@ -7,7 +7,10 @@
 //     attention is < 1% of the prefill FLOPs at the BASELINE sequence lengths; the tcgen05 port is DESIGN.md "next").
 // (2) decode_attn_kernel: single-query paged-KV attention for greedy decode.  One CTA per (kv head, context split);
 //     the 4 query heads of a GQA group share every K/V load; 8-lane groups own one key each and reduce with warp
-//     shuffles; splits are merged by the last CTA to finish (self-resetting ticket).
+//     shuffles.  Under programmatic dependent launch the cached K/V rows are fetched ahead of the dependency wait
+//     (only q and the newest row come from the QKV kernel).  Splits are merged all-to-all through tagged 64-bit
+//     words, each CTA owning a slice of the outputs (TAGGED = true; latency chain of one publish + one poll), or by
+//     the last CTA to take a ticket (TAGGED = false: odd split counts, grids too large to be resident at once).
 //
 // Reference call sites: flash_attn_varlen_qkvpacked_func (internvit/flash_attention.py:61) / naive softmax
 // (modeling_intern_vit.py:170-174); whale attention.py:391-415; transformers sdpa/eager attention

@@ -6,7 +6,9 @@
 // TMA-loaded with the 128B swizzle) and the activation vector is row 0 of a 16 x 64 *N* operand tile, so the CUDA
 // cores only run the per-row epilogue:
 //   warp 0  TMA producer: streams W tiles into an smem ring (starts before the PDL dependency resolves: weights
-//           never depend on the previous kernel, except for the expert ids which it waits for);
+//           never depend on the previous kernel, except for the expert ids which it waits for); once its last tile is
+//           issued it triggers the dependent launch, so the next kernel of the chain sets up and fills its own ring
+//           while this one drains and reduces;
 //   warp 1  MMA issuer: per ring stage, 4 x tcgen05.mma.kind::f16 (M=128, N=16, K=16) per part into TMEM;
 //   warp 2  TMEM allocator;
 //   warp 3  x-tile writer: copies 128 B of the (bf16, smem-resident) activation vector into row 0 of the stage's
@@ -14,8 +16,9 @@
 //   warps 4-7  prologue (RMSNorm / router / residual prefetch) and epilogue: tcgen05.ld, fused per-row epilogue.
 // Work is cut stream-K style: the (row-block, k-block) units are split evenly and contiguously over the CTAs, so all
 // 148 SMs stream the same number of bytes whatever the matrix shape.  A row block whose K range spans several CTAs
-// is combined through per-contributor scratch slots and a ticket; the last contributor sums the slots in a fixed
-// order (deterministic) and runs the epilogue.
+// is combined through per-contributor slots of 64-bit {partial, tag} words: no fence and no atomic, the CTA that ends
+// on the row block polls the others' words (collecting early arrivals while its own MMAs still run), adds them in
+// slot order (deterministic), clears the tags and runs the epilogue.
 #include "common.h"
 #include "ptx.cuh"
 
