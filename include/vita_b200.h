@@ -83,7 +83,10 @@ int vita_attention_fwd(const void* q, const void* k, const void* v, void* o, con
                        int64_t n_q_heads, int64_t n_kv_heads, int64_t Sq, int64_t Skv, int64_t d_qk, int64_t d_v,
                        const int32_t* kv_lens, int causal, float scale, void* stream);
 /* single-query paged-KV attention for decode (vLLM paged Attention, mixtral.py:484-501).  workspace must be
- * zero-initialised once and be at least vita_decode_attention_workspace_bytes() large. */
+ * zero-initialised once and be at least vita_decode_attention_workspace_bytes() large for the largest (B, splits) it
+ * is used with; every launch hands it back all-zero, so B and splits may change from call to call.  The context
+ * splits of a kv head are merged all-to-all through tagged 64-bit words when splits is 4, 8 or 16 and the grid is
+ * resident at once, otherwise by the last CTA to take a ticket ("attn_tagged"). */
 int64_t vita_decode_attention_workspace_bytes(int64_t B, int64_t n_kv_heads, int64_t splits);
 int vita_decode_attention(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table,
                           const int32_t* cur_pos, void* out, void* workspace, int64_t B, int64_t n_q_heads,

@@ -636,6 +636,11 @@ decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
                 ms[s] = -INFINITY; ls[s] = 0.0f; os[s] = 0.0f;
             }
         }
+        // consumed: hand the workspace back all-zero (the tagged variant shares it and reads a non-zero upper half
+        // of an 8-byte word as "published"; each element below was read by this thread only)
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s)
+            if (s < p.splits) __stcg(&p.part_o[(sbase + s * DEC_GROUP + h) * DEC_D + d], 0.0f);
         float mm = -INFINITY;
 #pragma unroll
         for (int s = 0; s < MAXS; ++s) mm = fmaxf(mm, ms[s]);
@@ -649,6 +654,8 @@ decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
         p.out[(static_cast<long long>(b) * p.n_q + kvh * DEC_GROUP + h) * DEC_D + d] =
             __float2bfloat16(ll > 0.0f ? oo / ll : 0.0f);
     }
+    __syncthreads();   // every thread has read the (m, l) pairs
+    if (d < p.splits * DEC_GROUP * 2) __stcg(&p.part_ml[sbase * 2 + d], 0.0f);
     if (threadIdx.x == 0) VITA_STAMP(8);
 }
 
@@ -688,7 +695,9 @@ extern "C" int vita_attention_fwd(const void* q, const void* k, const void* v, v
 }
 
 extern "C" int64_t vita_decode_attention_workspace_bytes(int64_t B, int64_t n_kv_heads, int64_t splits) {
-    // 8-byte words {value, tag} for the split partials (the ticket variant uses the same buffer as plain floats)
+    // 8-byte words {value, tag} for the split partials; the ticket variant uses the front of the same buffer as plain
+    // floats.  Invariant kept by both variants: the workspace is all-zero between launches (tags cleared by their
+    // readers, floats zeroed by the merging CTA, tickets reset), so calls may change B / splits / variant freely.
     const int64_t n = B * n_kv_heads * splits * DEC_GROUP;
     return n * DEC_D * 8 + B * n_kv_heads * splits * splits * DEC_GROUP * 2 * 8 + ((B * n_kv_heads * 4 + 255) / 256) * 256 + 256;
 }
