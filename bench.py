@@ -238,8 +238,8 @@ def run_reference(args):
 def workload_config(cfg, args, n):
     return {"workload": "configs[2]: 1 image (448x448, 1 tile) + 10 s audio (998 fbank frames) + 126 text tokens -> "
                         f"S={spliced_len(cfg)} omni prefill -> {args.new_tokens}-token greedy decode, bs=1 per GPU",
-            "model": f"Mixtral-8x7B geometry ({cfg.llm.num_hidden_layers} layers, H=4096, I=14336, 8 experts top-2, "
-                     "V=51760) + InternViT-300M + Whale, random init",
+            "geometry": f"Mixtral-8x7B ({cfg.llm.num_hidden_layers} layers, H=4096, I=14336, 8 experts top-2, "
+                        "V=51760) + InternViT-300M + Whale, random init",
             "parallelism": f"replica x{n} (request parallel; the model fits one 180 GB B200)",
             "l2_policy": "inputs larger than L2 (93.7 GB of weights streamed every step)"}
 
