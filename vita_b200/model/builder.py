@@ -44,16 +44,75 @@ def config_from_hf(cfg_json: dict) -> VitaConfig:
     return VitaConfig(llm=llm, vision=vision, audio=audio)
 
 
-def _load_safetensors_dir(path: Path) -> dict:
-    from safetensors import safe_open
-    state = {}
-    for shard in sorted(path.glob("*.safetensors")):
-        with safe_open(str(shard), framework="pt", device="cpu") as f:
-            for k in f.keys():
-                state[k] = f.get_tensor(k)
-    if not state:
-        raise ValueError(f"no *.safetensors shards under {path}")
-    return state
+class LazySafetensors:
+    """Read-only mapping over the `*.safetensors` shards of a checkpoint directory that reads a tensor only when it is
+    asked for.  `weights.pack` walks the model layer by layer and moves every tensor to the GPU as soon as it has it,
+    so the host never holds more than one layer of the 93.7 GB checkpoint instead of the
+    whole state dict.  Uses `model.safetensors.index.json` when present, else the shards' own key lists."""
+
+    def __init__(self, path: Path, prefix: str = ""):
+        from safetensors import safe_open
+        self._open = safe_open
+        self._prefix = prefix
+        self._where = {}
+        index = path / "model.safetensors.index.json"
+        if index.exists():
+            for k, shard in json.loads(index.read_text())["weight_map"].items():
+                self._where[prefix + k] = path / shard
+        else:
+            for shard in sorted(path.glob("*.safetensors")):
+                with safe_open(str(shard), framework="pt", device="cpu") as f:
+                    for k in f.keys():
+                        self._where[prefix + k] = shard
+        if not self._where:
+            raise ValueError(f"no *.safetensors shards under {path}")
+        self._handles = {}
+
+    def __contains__(self, key) -> bool:
+        return key in self._where
+
+    def __iter__(self):
+        return iter(self._where)
+
+    def __len__(self) -> int:
+        return len(self._where)
+
+    def keys(self):
+        return self._where.keys()
+
+    def __getitem__(self, key):
+        shard = self._where[key]                       # KeyError for unknown names, like a dict
+        f = self._handles.get(shard)
+        if f is None:
+            f = self._handles[shard] = self._open(str(shard), framework="pt", device="cpu").__enter__()
+        return f.get_tensor(key[len(self._prefix):])
+
+    def close(self):
+        for f in self._handles.values():
+            f.__exit__(None, None, None)
+        self._handles.clear()
+
+
+class _Overlay:
+    """`primary` wins over `base` for the keys it has (the reference's separate vision-tower checkpoint override,
+    vita/model/builder.py:245-257)."""
+
+    def __init__(self, primary, base):
+        self.primary, self.base = primary, base
+
+    def __contains__(self, key):
+        return key in self.primary or key in self.base
+
+    def __getitem__(self, key):
+        return self.primary[key] if key in self.primary else self.base[key]
+
+    def __iter__(self):
+        yield from self.primary
+        yield from (k for k in self.base if k not in self.primary)
+
+
+def _load_safetensors_dir(path: Path) -> LazySafetensors:
+    return LazySafetensors(path)
 
 
 def load_pretrained_model(model_path, model_base=None, model_name=None, model_type="mixtral-8x7b", load_8bit=False,
@@ -74,11 +133,12 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, model_ty
     path = Path(model_path)
     cfg = config_from_hf(json.loads((path / "config.json").read_text()))
     state = _load_safetensors_dir(path)
-    vt = getattr(kwargs, "vision_tower_path", None) or kwargs.get("vision_tower_path")
+    vt = kwargs.get("vision_tower_path")
     if vt:                                                                        # builder.py:245-257 override
-        for k, t in _load_safetensors_dir(Path(vt)).items():
-            state[W.PREFIX_VISION + k] = t
+        state = _Overlay(LazySafetensors(Path(vt), prefix=W.PREFIX_VISION), state)
     model = VITAMixtralForCausalLM(cfg, W.pack(state, cfg, dev), dev, **model_kwargs)
+    for s_ in (state.primary, state.base) if isinstance(state, _Overlay) else (state,):
+        s_.close()
     tokenizer = image_processor = None
     try:
         from transformers import AutoTokenizer
