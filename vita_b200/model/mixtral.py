@@ -90,8 +90,7 @@ class MixtralDecoder:
                                        cfg.vocab_size, self.decode_splits, dev)
         self._graph = None
         self._graph_batch = None
-        self._bgraph = None
-        self._bgraph_B = None
+        self._bgraphs = {}            # batched decode step: captured CUDA graph per batch size
         self.d_slots = torch.zeros(B, dtype=torch.int32, device=dev)
         self._prefill_ws = {}
         # expert parallelism: this rank holds experts [e_lo, e_hi) of every layer; attention, router, embeddings and
@@ -139,7 +138,7 @@ class MixtralDecoder:
         if S > cap:
             c = self.cfg
             cap = max(S, 2 * cap, 128)
-            self._bgraph = None   # the batched-step graph references the old workspaces
+            self._bgraphs = {}    # the batched-step graphs reference the old workspaces
             H, I, E, dev = c.hidden_size, c.intermediate_size, c.num_local_experts, self.device
             self._prefill_ws = dict(
                 cap=cap,
@@ -376,7 +375,7 @@ class MixtralDecoder:
         if not use_graph:
             self._batched_step_kernels(B, False)
             return
-        if self._bgraph is None or self._bgraph_B != B:
+        if B not in self._bgraphs:             # one captured graph per batch size (continuous batching changes B)
             snap = self._save_state()
             self._batched_step_kernels(B, False)          # warm-up (cudaFuncSetAttribute etc.)
             torch.cuda.synchronize()
@@ -390,8 +389,8 @@ class MixtralDecoder:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self._restore_state(snap)
-            self._bgraph, self._bgraph_B = g, B
-        self._bgraph.replay()
+            self._bgraphs[B] = g
+        self._bgraphs[B].replay()
 
     def _save_state(self):
         c = self.cache
