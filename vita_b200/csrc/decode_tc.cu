@@ -528,7 +528,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
                             if (!(have & (1u << (p * TC_SLOTS + q)))) {
                                 unsigned long long w = ld_relaxed_u64(addr);
                                 for (uint32_t spin = 0; (w >> 32) == 0; ++spin) {
-                                    if (spin > (1u << 26)) __trap();   // a contributor never published
+                                    if (spin > (1u << 24)) __trap();   // a contributor never published (seconds, not minutes)
                                     w = ld_relaxed_u64(addr);
                                 }
                                 oth[p][q] = __uint_as_float(static_cast<uint32_t>(w));
