@@ -21,7 +21,7 @@ def _ref_attn(q, k, v, scale, causal, kv_lens=None):
     return torch.matmul(torch.softmax(s, -1), v)
 
 
-@pytest.mark.parametrize("S", [1, 63, 64, 65, 200, 513])
+@pytest.mark.parametrize("S", [1, 63, 64, 65, 128, 129, 200, 513, 1025, 4096])
 def test_mixtral_causal_gqa(S):
     from vita_b200 import ops
     nq, nkv, D = 8, 2, 128

@@ -64,6 +64,11 @@ static Option g_options[] = {
     {"tc_trigger_lead", "VITA_B200_TC_TRIGGER_LEAD", 0, {-1}},
     // tcgen05 decode kernels: pull norm / router weights into L2 ahead of the dependency wait
     {"tc_prefetch_consts", "VITA_B200_TC_PREFETCH_CONSTS", 1, {-1}},
+    // FlashAttention (flash_tc.cu): force the number of query tiles per CTA (0 = heuristic, 1, 2)
+    {"fa_nq", "VITA_B200_FA_NQ", 0, {-1}},
+    // bring-up aids: override the MN-major V descriptor strides in bytes (0 = derived from the tile shape)
+    {"fa_v_lbo", "VITA_B200_FA_V_LBO", 0, {-1}},
+    {"fa_v_sbo", "VITA_B200_FA_V_SBO", 0, {-1}},
 };
 
 int option(const char* name) {

@@ -1,11 +1,6 @@
-// Attention kernels.
+// Paged decode attention (the prefill-shaped FlashAttention lives in flash_tc.cu).
 //
-// (1) flash_fwd_kernel<DQK, DV>: FlashAttention-style fused softmax(Q K^T * scale) V for the three prefill-shaped
-//     attentions of the path: Mixtral causal GQA (128/128), InternViT non-causal (64/64), Whale rel-pos with the two
-//     score terms folded into one contraction over [k | p] (128/64).  K/V tiles are staged through XOR-swizzled shared
-//     memory with cp.async double buffering; the contractions run on mma.sync m16n8k16 bf16 (legacy tensor path --
-//     attention is < 1% of the prefill FLOPs at the BASELINE sequence lengths; the tcgen05 port is DESIGN.md "next").
-// (2) decode_attn_kernel: single-query paged-KV attention for greedy decode.  One CTA per (kv head, context split);
+// decode_attn_kernel: single-query paged-KV attention for greedy decode.  One CTA per (kv head, context split);
 //     the 4 query heads of a GQA group share every K/V load; 8-lane groups own one key each and reduce with warp
 //     shuffles.  Under programmatic dependent launch the cached K/V rows are fetched ahead of the dependency wait
 //     (only q and the newest row come from the QKV kernel).  Splits are merged all-to-all through tagged 64-bit
@@ -19,252 +14,6 @@
 #include "ptx.cuh"
 
 namespace vita {
-
-struct AttnParams {
-    const __nv_bfloat16* q;
-    const __nv_bfloat16* k;
-    const __nv_bfloat16* v;
-    __nv_bfloat16* o;
-    long long q_bs, q_ts, q_hs;  // batch / token / head strides in elements
-    long long k_bs, k_ts, k_hs;
-    long long v_bs, v_ts, v_hs;
-    long long o_bs, o_ts, o_hs;
-    int group;         // query heads per kv head
-    int Sq, Skv;
-    const int* kv_lens;  // [B] valid keys per batch entry, or nullptr
-    int causal;
-    float scale_log2;  // softmax scale * log2(e)
-};
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
-    const int sz = pred ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-        "{%0, %1, %2, %3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// byte offset of 16-byte chunk `chunk` of row `row` in a [rows][D] bf16 tile with XOR swizzle
-template <int D>
-__device__ __forceinline__ uint32_t swz(int row, int chunk) {
-    return static_cast<uint32_t>(row * D * 2 + ((chunk ^ (row & 7)) << 4));
-}
-
-template <int D, int ROWS, int THREADS>
-__device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_bfloat16* g, long long tok_stride,
-                                                int row0, int n_valid_rows) {
-    constexpr int CPR = D / 8;  // chunks per row
-    constexpr int TOTAL = ROWS * CPR;
-#pragma unroll
-    for (int i = 0; i < TOTAL / THREADS; ++i) {
-        const int c = threadIdx.x + i * THREADS;
-        const int r = c / CPR, ch = c % CPR;
-        const bool ok = (row0 + r) < n_valid_rows;
-        const __nv_bfloat16* src = g + static_cast<long long>(ok ? (row0 + r) : 0) * tok_stride + ch * 8;
-        cp_async16(smem_base + swz<D>(r, ch), src, ok);
-    }
-}
-
-// BM query rows per CTA (BM / 16 warps); K/V tiles of 64 keys.  BM = 128 halves the K/V shared-memory traffic per FLOP
-// (used for long sequences), BM = 64 keeps enough CTAs in flight for short ones.
-template <int DQK, int DV, int BM>
-__global__ void __launch_bounds__(BM * 2)
-flash_fwd_kernel(const AttnParams p) {
-    constexpr int THREADS = BM * 2;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t sQ = smem_u32(smem);
-    const uint32_t sK = sQ + BM * DQK * 2;
-    const uint32_t sV = sK + 2 * 64 * DQK * 2;
-
-    const int m_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-    const int kvh = head / p.group;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int kv_len = p.kv_lens ? p.kv_lens[b] : p.Skv;
-    if (kv_len > p.Skv) kv_len = p.Skv;
-    const int q0 = m_blk * BM;
-    int n_tiles = (kv_len + 63) / 64;
-    if (p.causal && n_tiles > (q0 + BM + 63) / 64) n_tiles = (q0 + BM + 63) / 64;
-
-    const __nv_bfloat16* qg = p.q + b * p.q_bs + head * p.q_hs;
-    const __nv_bfloat16* kg = p.k + b * p.k_bs + kvh * p.k_hs;
-    const __nv_bfloat16* vg = p.v + b * p.v_bs + kvh * p.v_hs;
-
-    load_tile_async<DQK, BM, THREADS>(sQ, qg, p.q_ts, q0, p.Sq);
-    if (n_tiles > 0) {
-        load_tile_async<DQK, 64, THREADS>(sK, kg, p.k_ts, 0, kv_len);
-        load_tile_async<DV, 64, THREADS>(sV, vg, p.v_ts, 0, kv_len);
-    }
-    cp_async_commit();
-
-    float o_acc[DV / 8][4];
-#pragma unroll
-    for (int i = 0; i < DV / 8; ++i)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o_acc[i][e] = 0.0f;
-    float m_i[2] = {-INFINITY, -INFINITY};
-    float l_i[2] = {0.0f, 0.0f};
-    uint32_t q_frag[DQK / 16][4];
-
-    const int g = lane >> 2, tq = lane & 3;
-    const int ld_i = lane >> 3, ld_r = lane & 7;
-
-    for (int j = 0; j < n_tiles; ++j) {
-        const int buf = j & 1;
-        if (j + 1 < n_tiles) {
-            load_tile_async<DQK, 64, THREADS>(sK + (buf ^ 1) * 64 * DQK * 2, kg, p.k_ts, (j + 1) * 64, kv_len);
-            load_tile_async<DV, 64, THREADS>(sV + (buf ^ 1) * 64 * DV * 2, vg, p.v_ts, (j + 1) * 64, kv_len);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        if (j == 0) {
-#pragma unroll
-            for (int ks = 0; ks < DQK / 16; ++ks)
-                ldsm_x4(sQ + swz<DQK>(warp * 16 + (ld_i & 1) * 8 + ld_r, ks * 2 + (ld_i >> 1)), q_frag[ks][0],
-                        q_frag[ks][1], q_frag[ks][2], q_frag[ks][3]);
-        }
-        const uint32_t kb = sK + buf * 64 * DQK * 2;
-        const uint32_t vb = sV + buf * 64 * DV * 2;
-
-        float s[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) s[i][e] = 0.0f;
-#pragma unroll
-        for (int ks = 0; ks < DQK / 16; ++ks) {
-#pragma unroll
-            for (int nt2 = 0; nt2 < 4; ++nt2) {
-                uint32_t r0, r1, r2, r3;
-                ldsm_x4(kb + swz<DQK>(nt2 * 16 + (ld_i >> 1) * 8 + ld_r, ks * 2 + (ld_i & 1)), r0, r1, r2, r3);
-                mma16816(s[nt2 * 2], q_frag[ks], r0, r1);
-                mma16816(s[nt2 * 2 + 1], q_frag[ks], r2, r3);
-            }
-        }
-
-        // scale, mask, online softmax (base 2)
-        const int row_lo = q0 + warp * 16 + g;
-        float rmax[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int col = j * 64 + nt * 8 + tq * 2 + (e & 1);
-                const int row = row_lo + (e >> 1) * 8;
-                float v = s[nt][e] * p.scale_log2;
-                if (col >= kv_len || (p.causal && col > row)) v = -INFINITY;
-                s[nt][e] = v;
-                rmax[e >> 1] = fmaxf(rmax[e >> 1], v);
-            }
-        }
-        float alpha[2], m_safe[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 1));
-            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 2));
-            const float m_new = fmaxf(m_i[r], rmax[r]);
-            m_safe[r] = (m_new == -INFINITY) ? 0.0f : m_new;
-            alpha[r] = exp2f(m_i[r] - m_safe[r]);
-            m_i[r] = m_new;
-        }
-        float rsum[2] = {0.0f, 0.0f};
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float pv = exp2f(s[nt][e] - m_safe[e >> 1]);
-                s[nt][e] = pv;
-                rsum[e >> 1] += pv;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) l_i[r] = l_i[r] * alpha[r] + rsum[r];
-#pragma unroll
-        for (int dt = 0; dt < DV / 8; ++dt) {
-            o_acc[dt][0] *= alpha[0];
-            o_acc[dt][1] *= alpha[0];
-            o_acc[dt][2] *= alpha[1];
-            o_acc[dt][3] *= alpha[1];
-        }
-        // O += P V
-#pragma unroll
-        for (int ks2 = 0; ks2 < 4; ++ks2) {
-            uint32_t a[4];
-            a[0] = pack_bf16(s[ks2 * 2][0], s[ks2 * 2][1]);
-            a[1] = pack_bf16(s[ks2 * 2][2], s[ks2 * 2][3]);
-            a[2] = pack_bf16(s[ks2 * 2 + 1][0], s[ks2 * 2 + 1][1]);
-            a[3] = pack_bf16(s[ks2 * 2 + 1][2], s[ks2 * 2 + 1][3]);
-#pragma unroll
-            for (int dt2 = 0; dt2 < DV / 16; ++dt2) {
-                uint32_t r0, r1, r2, r3;
-                ldsm_x4_t(vb + swz<DV>(ks2 * 16 + (ld_i & 1) * 8 + ld_r, dt2 * 2 + (ld_i >> 1)), r0, r1, r2, r3);
-                mma16816(o_acc[dt2 * 2], a, r0, r1);
-                mma16816(o_acc[dt2 * 2 + 1], a, r2, r3);
-            }
-        }
-        __syncthreads();
-    }
-    cp_async_wait<0>();
-
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
-        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
-    }
-    __nv_bfloat16* og = p.o + b * p.o_bs + head * p.o_hs;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int row = q0 + warp * 16 + g + r * 8;
-        if (row >= p.Sq) continue;
-        const float inv = l_i[r] > 0.0f ? 1.0f / l_i[r] : 0.0f;
-        __nv_bfloat16* orow = og + static_cast<long long>(row) * p.o_ts;
-#pragma unroll
-        for (int dt = 0; dt < DV / 8; ++dt) {
-            const uint32_t packed = pack_bf16(o_acc[dt][r * 2] * inv, o_acc[dt][r * 2 + 1] * inv);
-            *reinterpret_cast<uint32_t*>(orow + dt * 8 + tq * 2) = packed;
-        }
-    }
-}
-
-template <int DQK, int DV, int BM>
-static int launch_flash_bm(const AttnParams& p, int B, int Hq, cudaStream_t st) {
-    constexpr int smem_bytes = BM * DQK * 2 + 2 * 64 * DQK * 2 + 2 * 64 * DV * 2;
-    static bool configured = false;
-    auto kern = flash_fwd_kernel<DQK, DV, BM>;
-    if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
-                            "cudaFuncSetAttribute(flash smem)");
-        if (rc) return rc;
-        configured = true;
-    }
-    dim3 grid((p.Sq + BM - 1) / BM, Hq, B);
-    kern<<<grid, BM * 2, smem_bytes, st>>>(p);
-    return check_launch("flash_fwd_kernel");
-}
-
-template <int DQK, int DV>
-static int launch_flash(const AttnParams& p, int B, int Hq, cudaStream_t st) {
-    // 128-row CTAs once they still fill the machine twice over
-    const long long ctas128 = static_cast<long long>((p.Sq + 127) / 128) * Hq * B;
-    if (ctas128 >= 2ll * num_sms()) return launch_flash_bm<DQK, DV, 128>(p, B, Hq, st);
-    return launch_flash_bm<DQK, DV, 64>(p, B, Hq, st);
-}
 
 // ------------------------------------------------------------------------------------------------ paged decode
 constexpr int DEC_D = 128;     // head dim
@@ -662,37 +411,6 @@ decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
 }  // namespace vita
 
 using namespace vita;
-
-extern "C" int vita_attention_fwd(const void* q, const void* k, const void* v, void* o, const int64_t* q_strides,
-                                  const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
-                                  int64_t B, int64_t n_q_heads, int64_t n_kv_heads, int64_t Sq, int64_t Skv,
-                                  int64_t d_qk, int64_t d_v, const int32_t* kv_lens, int causal, float scale,
-                                  void* stream) {
-    VITA_REQUIRE(n_kv_heads > 0 && n_q_heads % n_kv_heads == 0, "n_q_heads must be a multiple of n_kv_heads");
-    VITA_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "q/k/v/o must be 16-byte aligned");
-    for (int i = 0; i < 3; ++i)
-        VITA_REQUIRE(q_strides[i] % 8 == 0 && k_strides[i] % 8 == 0 && v_strides[i] % 8 == 0 && o_strides[i] % 2 == 0,
-                     "strides must keep 16-byte row alignment");
-    if (B == 0 || Sq == 0) return VITA_OK;
-    AttnParams p{};
-    p.q = BF16C(q); p.k = BF16C(k); p.v = BF16C(v); p.o = static_cast<__nv_bfloat16*>(o);
-    p.q_bs = q_strides[0]; p.q_ts = q_strides[1]; p.q_hs = q_strides[2];
-    p.k_bs = k_strides[0]; p.k_ts = k_strides[1]; p.k_hs = k_strides[2];
-    p.v_bs = v_strides[0]; p.v_ts = v_strides[1]; p.v_hs = v_strides[2];
-    p.o_bs = o_strides[0]; p.o_ts = o_strides[1]; p.o_hs = o_strides[2];
-    p.group = static_cast<int>(n_q_heads / n_kv_heads);
-    p.Sq = static_cast<int>(Sq);
-    p.Skv = static_cast<int>(Skv);
-    p.kv_lens = kv_lens;
-    p.causal = causal;
-    p.scale_log2 = scale * 1.4426950408889634f;
-    auto st = static_cast<cudaStream_t>(stream);
-    if (d_qk == 128 && d_v == 128) return launch_flash<128, 128>(p, (int)B, (int)n_q_heads, st);
-    if (d_qk == 64 && d_v == 64) return launch_flash<64, 64>(p, (int)B, (int)n_q_heads, st);
-    if (d_qk == 128 && d_v == 64) return launch_flash<128, 64>(p, (int)B, (int)n_q_heads, st);
-    set_last_error("vita_attention_fwd: unsupported head dims (supported: 128/128, 64/64, 128/64)");
-    return VITA_ERR_INVALID;
-}
 
 extern "C" int64_t vita_decode_attention_workspace_bytes(int64_t B, int64_t n_kv_heads, int64_t splits) {
     // 8-byte words {value, tag} for the split partials; the ticket variant uses the front of the same buffer as plain
