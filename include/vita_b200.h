@@ -77,11 +77,13 @@ int vita_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_
 /* softmax(Q K^T * scale [causal] [kv_lens mask]) V, FlashAttention style.  Strides are {batch, token, head} in
  * elements.  Supported (d_qk, d_v): (128,128) Mixtral GQA, (64,64) InternViT, (128,64) Whale rel-pos with the
  * operands prepared by vita_whale_qk_prep.  Replaces flash_attn_varlen_qkvpacked_func
- * (internvit/flash_attention.py:61), whale attention.py:391-415, transformers sdpa (modeling_mixtral.py:269-292). */
+ * (internvit/flash_attention.py:61), whale attention.py:391-415, transformers sdpa (modeling_mixtral.py:269-292).
+ * causal: query row i attends keys <= q_pos0 + i (q_pos0 = 0 for a whole sequence; a sequence shard passes the
+ * position of its first row). */
 int vita_attention_fwd(const void* q, const void* k, const void* v, void* o, const int64_t* q_strides,
                        const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides, int64_t B,
                        int64_t n_q_heads, int64_t n_kv_heads, int64_t Sq, int64_t Skv, int64_t d_qk, int64_t d_v,
-                       const int32_t* kv_lens, int causal, float scale, void* stream);
+                       const int32_t* kv_lens, int causal, int64_t q_pos0, float scale, void* stream);
 /* single-query paged-KV attention for decode (vLLM paged Attention, mixtral.py:484-501).  workspace must be
  * zero-initialised once and be at least vita_decode_attention_workspace_bytes() large for the largest (B, splits) it
  * is used with; every launch hands it back all-zero, so B and splits may change from call to call.  The context
@@ -125,10 +127,17 @@ int vita_moe_gemm_down_ep(const void* Act, const void* W_down, const int32_t* ex
                           const int32_t* row_assign, void* const* peer_out, int64_t rows, int64_t num_local_experts,
                           int64_t H, int64_t I, int64_t chunk, void* stream);
 int vita_ep_signal(void* const* peer_flags, int64_t which, int64_t n_ranks, int64_t my_rank, int64_t epoch, void* stream);
-int vita_ep_wait(const int32_t* my_flags, int64_t which, int64_t n_ranks, int64_t epoch, void* stream);
+/* waits for flags[which][src] >= epoch of the sources src < n_wait (n_wait = n_ranks: everybody) */
+int vita_ep_wait(const int32_t* my_flags, int64_t which, int64_t n_ranks, int64_t n_wait, int64_t epoch, void* stream);
+/* gather = 1: the reduced rows go to every rank's h / xn; gather = 0: to this rank's only (sequence-sharded stream) */
 int vita_ep_reduce_norm_gather(const void* rs_buf, const int32_t* my_flags, void* const* peer_h, void* const* peer_xn,
                                const void* next_norm_w, int64_t tok0, int64_t n_owned, int64_t n_ranks, int64_t my_rank,
-                               int64_t epoch, int64_t H, float eps, void* stream);
+                               int64_t epoch, int64_t H, float eps, int64_t gather, void* stream);
+/* all-gather by P2P stores: up to 4 byte ranges [offset, offset + bytes) of this rank's symmetric buffer
+ * (peer_base[my_rank]) are copied to the same offsets of every other rank's buffer.  Offsets are multiples of 16,
+ * sizes of 4.  Used for the K/V rows and the routed activations of a sequence shard. */
+int vita_ep_push(void* const* peer_base, const int64_t* offsets, const int64_t* bytes, int64_t n_ranges,
+                 int64_t n_ranks, int64_t my_rank, void* stream);
 
 /* expert-parallel tail of a decoder layer (NCCL variant): h += y where y is the all-reduced sum of the ranks' partial MoE outputs
  * (each rank ran vita_moe_combine on a zeroed buffer with only its local experts' rows filled); optional next RMSNorm. */
@@ -187,9 +196,11 @@ int vita_whale_adapter_im2col(const void* x, const int32_t* lengths, void* out, 
                               int64_t ksize, void* stream);
 
 /* ---- greedy decode step (weight-streaming GEMVs) ---------------------------------------------------------- */
-/* consume the previous arg-max (best[b]), append it to token_log, advance cache_len, gather its embedding. */
+/* consume the previous arg-max (best[b]), append it to token_log, advance cache_len, gather its embedding.
+ * max_ctx = KV capacity per sequence (pages * page_size): cur_pos saturates at max_ctx - 1. */
 int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* gen_count, int64_t max_log, int32_t* cache_len,
-                      int32_t* cur_pos, const void* embed, void* h, int64_t B, int64_t H, int64_t vocab, void* stream);
+                      int32_t* cur_pos, const void* embed, void* h, int64_t B, int64_t H, int64_t vocab,
+                      int64_t max_ctx, void* stream);
 /* input_layernorm + fused q/k/v projection + RoPE + paged-KV append for one token per sequence. */
 int vita_decode_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, const float* cos_sin,
                          const int32_t* cur_pos, const int32_t* block_table, void* q_out, void* k_cache, void* v_cache,

@@ -56,7 +56,7 @@ def main():
                 ops.set_option(k, v)
             for k, v in attrs.items():
                 setattr(llm, k, v)
-            llm._graph = None
+            llm._graphs = {}
             llm.attn_ws.zero_()     # the two split-merge protocols use the same buffer differently
             llm.reset()
             llm.prefill(emb.clone(), slot=0)

@@ -48,7 +48,7 @@ def main():
     buf = torch.zeros(n_rec, 32, dtype=torch.int64, device=dev)
     lib.vita_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_int64]
     lib.vita_debug_trace(buf.data_ptr(), n_rec)     # serial restarts: the captured launches use records 0..
-    llm._graph = None
+    llm._graphs = {}
     for _ in range(4):
         llm.decode_step(1, use_graph=True)          # first call: eager warm-up + capture, then replays
     torch.cuda.synchronize()

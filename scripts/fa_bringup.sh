@@ -22,3 +22,6 @@ run VITA_B200_FA_NQ=1 VITA_B200_FA_V_LBO=16384 VITA_B200_FA_V_SBO=2048 python sc
 timeout 900 python -m pytest tests/test_attention_gpu.py -x -q >> $L 2>&1
 echo "pytest attention rc=$?" >> $L
 tail -60 $L
+timeout 900 python -m pytest tests/test_demo_replay_gpu.py tests/test_decode_gpu.py -x -q > gpurun_out/demo_replay.log 2>&1
+echo "pytest demo rc=$?" >> gpurun_out/demo_replay.log
+tail -30 gpurun_out/demo_replay.log

@@ -132,8 +132,13 @@ def test_decode_embed_bookkeeping():
     clen = torch.tensor([10, 20, 30], dtype=torch.int32, device="cuda")
     cur = torch.zeros(B, dtype=torch.int32, device="cuda")
     h = torch.zeros(B, H, dtype=BF16, device="cuda")
-    ops.decode_embed(best, log, cnt, clen, cur, to_dev(embed), h)
+    ops.decode_embed(best, log, cnt, clen, cur, to_dev(embed), h, 31)    # KV capacity 31: the third sequence is full - 1
     assert torch.equal(h.float().cpu(), embed[toks])
     assert cur.cpu().tolist() == [10, 20, 30] and clen.cpu().tolist() == [11, 21, 31]
+    # a full cache saturates instead of indexing past the block-table row / rope table
+    best.copy_(torch.tensor([(1 << 32) | (0xFFFFFFFF - 1)] * B, dtype=torch.int64))
+    ops.decode_embed(best, log, cnt, clen, cur, to_dev(embed), h, 31)
+    assert cur.cpu().tolist() == [11, 21, 30] and clen.cpu().tolist() == [12, 22, 31]
+    cnt.copy_(torch.tensor([1, 2, 4], dtype=torch.int32)); clen.copy_(torch.tensor([11, 21, 31], dtype=torch.int32))
     assert cnt.cpu().tolist() == [1, 2, 4] and best.cpu().tolist() == [0, 0, 0]
     assert log.cpu().tolist() == [[7, -1, -1, -1], [-1, 99, -1, -1], [-1, -1, -1, 0]]

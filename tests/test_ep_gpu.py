@@ -1,6 +1,7 @@
 """Expert-parallel prefill vs the single-GPU model with identical weights; needs >= 2 GPUs (gpurun --gpus 2).
-  p2p : the down-projection GEMM epilogue pushes rows to the token owners over NVLink peer memory (fused)
-  nccl: partial sums + one NCCL all-reduce per layer (baseline)"""
+  seq : sequence-sharded dense part + all-gathered K/V and routed rows + fused P2P combine (default; bit-identical)
+  p2p : replicated dense part, the down-projection GEMM epilogue pushes rows to the token owners (bit-identical)
+  nccl: partial sums + one NCCL all-reduce per layer (library baseline, statistical bound)"""
 import os
 import subprocess
 import sys
@@ -13,7 +14,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,port", [("p2p", 29533), ("nccl", 29534)])
+@pytest.mark.parametrize("mode,port", [("seq", 29532), ("p2p", 29533), ("nccl", 29534)])
 def test_ep2_prefill_matches_single_gpu(mode, port):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")

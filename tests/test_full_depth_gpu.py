@@ -1,0 +1,53 @@
+"""Full-depth check of the benchmarked configuration (BASELINE configs[2]): full-size InternViT + Whale + projector
++ splice, then all 32 Mixtral layers, against the fp32 oracle run layer-streamed on the same GPU (tests/full_depth.py).
+Needs ~110 GB of device memory (93.7 GB of bf16 weights + one fp32 layer)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_configs2_full_depth_prefill_and_greedy_vs_streamed_fp32_oracle():
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs a 180 GB device")
+    from oracle import vita_oracle as O
+    from tests.full_depth import check_mixtral
+    from tests.util import assert_close
+    from vita_b200 import weights as W
+    from vita_b200.config import VitaConfig, IMAGE_TOKEN_INDEX, AUDIO_TOKEN_INDEX
+    from vita_b200.model.vita_mixtral import VITAMixtralForCausalLM
+    cfg = VitaConfig.full(32)
+    dev = torch.device("cuda")
+    enc_state = W.synthetic_state(cfg, 0, parts=("vision", "projector", "audio"))
+    packed = W.random_packed(cfg, dev, seed=0, parts=("llm",))
+    packed["vision"] = W.pack_vision(enc_state, cfg, dev)
+    packed["projector"] = W.pack_projector(enc_state, cfg, dev)
+    packed["audio"] = W.pack_audio(enc_state, cfg, dev)
+    model = VITAMixtralForCausalLM(cfg, packed, dev, max_seq_len=1024, max_new_tokens=32)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, cfg.llm.vocab_size, (1, 128), generator=g)
+    ids[0, 1], ids[0, 2] = IMAGE_TOKEN_INDEX, AUDIO_TOKEN_INDEX
+    images = torch.randn(1, 3, 448, 448, generator=g)
+    feats = torch.randn(1, 998, 80, generator=g)
+    audios = {"audios": feats, "lengths": torch.tensor([998])}
+    # (1) full-size encoders + splice: the CUDA path's spliced embeddings vs the oracle's (fp32, on the GPU)
+    emb = model.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, images, audios)[4]
+    assert emb.shape == (1, 506, cfg.llm.hidden_size)
+    with torch.device(dev):
+        st = {k: v.to(dev) for k, v in enc_state.items()}
+        st["model.embed_tokens.weight"] = packed["llm"]["embed"]
+        ref_emb, lens = O.prepare_inputs_embeds(st, cfg, ids.to(dev), images.to(dev),
+                                                {"audios": feats.to(dev), "lengths": audios["lengths"].to(dev)})
+    assert lens == [506]
+    assert_close(emb, ref_emb, rel=4e-2, what="full-size spliced inputs_embeds (InternViT 24L + Whale 24L + adapter)")
+    del st
+    # (2) 32 layers: prefill last-row logits + 8 free-running greedy tokens
+    r = check_mixtral(model, emb[0], n_tokens=8)
+    print(r)
+    assert r["first_row_rel_err"] < 6e-2
+    assert r["max_row_rel_err_on_common_prefix"] < 8e-2
+    # ids: equal up to the first step where the oracle itself has a near-tie (random-init weights: flat distributions)
+    clear = 0
+    while clear < 8 and r["oracle_top2_rel_gap"][clear] > 0.08:
+        clear += 1
+    assert r["ids_equal_prefix"] >= clear, r

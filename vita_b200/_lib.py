@@ -28,7 +28,7 @@ SIGNATURES = {
     "vita_layernorm": (c_int, [P, P, P, P, I64, I64, c_float, c_int, c_float, P]),
     "vita_row_copy": (c_int, [P, P, P, P, I64, I64, P]),
     "vita_rope_kv_write": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
-    "vita_attention_fwd": (c_int, [P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P, c_int, c_float, P]),
+    "vita_attention_fwd": (c_int, [P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P, c_int, I64, c_float, P]),
     "vita_decode_attention_workspace_bytes": (I64, [I64, I64, I64]),
     "vita_decode_attention": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, I64, P]),
     "vita_decode_slots": (c_int, [P, P, P, I64, I64, I64, P]),
@@ -38,8 +38,9 @@ SIGNATURES = {
     "vita_moe_align": (c_int, [P, P, P, P, P, P, P, I64, I64, P]),
     "vita_moe_gemm_down_ep": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, I64, P]),
     "vita_ep_signal": (c_int, [P, I64, I64, I64, I64, P]),
-    "vita_ep_wait": (c_int, [P, I64, I64, I64, P]),
-    "vita_ep_reduce_norm_gather": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, I64, c_float, P]),
+    "vita_ep_wait": (c_int, [P, I64, I64, I64, I64, P]),
+    "vita_ep_push": (c_int, [P, P, P, I64, I64, I64, P]),
+    "vita_ep_reduce_norm_gather": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, I64, c_float, I64, P]),
     "vita_moe_gemm_gate_up_silu": (c_int, [P, P, P, P, I64, I64, I64, I64, P]),
     "vita_moe_gemm_down": (c_int, [P, P, P, P, P, I64, I64, I64, I64, P]),
     "vita_moe_combine": (c_int, [P, P, P, P, P, I64, I64, c_float, P]),
@@ -54,7 +55,7 @@ SIGNATURES = {
     "vita_whale_im2col2": (c_int, [P, P, I64, I64, I64, I64, P]),
     "vita_whale_qk_prep": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "vita_whale_adapter_im2col": (c_int, [P, P, P, I64, I64, I64, I64, P]),
-    "vita_decode_embed": (c_int, [P, P, P, I64, P, P, P, P, I64, I64, I64, P]),
+    "vita_decode_embed": (c_int, [P, P, P, I64, P, P, P, P, I64, I64, I64, I64, P]),
     "vita_decode_qkv_rope": (c_int, [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, P]),
     "vita_decode_oproj": (c_int, [P, P, P, I64, I64, I64, P]),
     "vita_decode_router": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_float, P]),

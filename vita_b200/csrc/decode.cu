@@ -542,7 +542,7 @@ static int launch_stream_gemv(const Op& op, int x_elems, int B, cudaStream_t st,
 // Start of a decode step: consume the previous arg-max, log it, advance the cache length, gather the embedding.
 __global__ void __launch_bounds__(256)
 decode_embed_kernel(unsigned long long* best, int* token_log, int* gen_count, int max_log, int* cache_len,
-                    int* cur_pos, const __nv_bfloat16* embed, __nv_bfloat16* h, int H, int vocab) {
+                    int* cur_pos, const __nv_bfloat16* embed, __nv_bfloat16* h, int H, int vocab, int max_ctx) {
     const int b = blockIdx.x;
     __shared__ int s_tok;
     pdl_launch_dependents();
@@ -555,8 +555,11 @@ decode_embed_kernel(unsigned long long* best, int* token_log, int* gen_count, in
         const int n = gen_count[b];
         if (n < max_log) token_log[static_cast<long long>(b) * max_log + n] = tok;
         gen_count[b] = n + 1;
-        cur_pos[b] = cache_len[b];
-        cache_len[b] = cache_len[b] + 1;
+        // a full cache stays full: the position saturates on the last slot instead of running into the next
+        // sequence's block-table row / beyond the rope table (the host refuses such requests up front)
+        const int len = cache_len[b];
+        cur_pos[b] = len < max_ctx ? len : max_ctx - 1;
+        cache_len[b] = len < max_ctx ? len + 1 : max_ctx;
         best[b] = 0ull;
     }
     __syncthreads();
@@ -694,13 +697,14 @@ extern "C" int vita_decode_slots(const int32_t* cur_pos, const int32_t* block_ta
 
 extern "C" int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* gen_count, int64_t max_log,
                                  int32_t* cache_len, int32_t* cur_pos, const void* embed, void* h, int64_t B,
-                                 int64_t H, int64_t vocab, void* stream) {
+                                 int64_t H, int64_t vocab, int64_t max_ctx, void* stream) {
     VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    VITA_REQUIRE(max_ctx > 0 && max_ctx <= 0x7fffffff, "max_ctx (KV capacity per sequence) must be positive");
     if (B == 0) return VITA_OK;
     cudaError_t e = launch_chain(decode_embed_kernel, dim3(static_cast<unsigned>(B)), dim3(256), 0,
                                  static_cast<cudaStream_t>(stream), reinterpret_cast<unsigned long long*>(best),
                                  token_log, gen_count, (int)max_log, cache_len, cur_pos, BF16C(embed),
-                                 static_cast<__nv_bfloat16*>(h), (int)H, (int)vocab);
+                                 static_cast<__nv_bfloat16*>(h), (int)H, (int)vocab, (int)max_ctx);
     if (e != cudaSuccess) return check_cuda(e, "decode_embed");
     return check_launch("decode_embed");
 }

@@ -432,8 +432,40 @@ __global__ void ep_signal_kernel(int* const* __restrict__ peer_flags, int which,
     }
 }
 
-__global__ void ep_wait_kernel(const int* __restrict__ my_flags, int which, int n_ranks, int epoch) {
-    if (threadIdx.x < n_ranks) sys_wait_flag(my_flags + which * n_ranks + threadIdx.x, epoch);
+__global__ void ep_wait_kernel(const int* __restrict__ my_flags, int which, int n_ranks, int n_wait, int epoch) {
+    if (threadIdx.x < n_wait) sys_wait_flag(my_flags + which * n_ranks + threadIdx.x, epoch);
+}
+
+// All-gather by P2P stores: byte ranges of this rank's symmetric buffer go to the same offsets of every peer.
+struct PushRanges {
+    long long off[4];
+    long long bytes[4];
+    int n;
+};
+__global__ void __launch_bounds__(256)
+ep_push_kernel(uint8_t* const* __restrict__ peer_base, const PushRanges r, int n_ranks, int my_rank) {
+    const uint8_t* src_base = peer_base[my_rank];
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (int i = 0; i < r.n; ++i) {
+        const uint4* src = reinterpret_cast<const uint4*>(src_base + r.off[i]);
+        const long long nvec = r.bytes[i] >> 4;
+        for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+            const uint4 x = src[v];
+            for (int d = 1; d < n_ranks; ++d) {      // start at a different peer per rank: spreads the NVSwitch ports
+                const int peer = (my_rank + d) % n_ranks;
+                reinterpret_cast<uint4*>(peer_base[peer] + r.off[i])[v] = x;
+            }
+        }
+        // tail of a range that is not a 16-byte multiple (e.g. an odd number of 8-byte routing records): 4-byte words
+        const long long tail0 = nvec << 4, nword = (r.bytes[i] - tail0) >> 2;
+        if (blockIdx.x == 0 && threadIdx.x < nword) {
+            const uint32_t x = *reinterpret_cast<const uint32_t*>(src_base + r.off[i] + tail0 + threadIdx.x * 4);
+            for (int d = 1; d < n_ranks; ++d) {
+                const int peer = (my_rank + d) % n_ranks;
+                *reinterpret_cast<uint32_t*>(peer_base[peer] + r.off[i] + tail0 + threadIdx.x * 4) = x;
+            }
+        }
+    }
 }
 
 // Owner side of the expert-parallel combine: for each owned token t (one block each)
@@ -445,7 +477,7 @@ __global__ void __launch_bounds__(THREADS)
 ep_reduce_norm_gather_kernel(const __nv_bfloat16* __restrict__ rs_buf, const int* __restrict__ my_flags,
                              __nv_bfloat16* const* __restrict__ peer_h, __nv_bfloat16* const* __restrict__ peer_xn,
                              const __nv_bfloat16* __restrict__ next_norm_w, int tok0, int n_ranks, int my_rank, int epoch,
-                             int H, float eps) {
+                             int H, float eps, int gather) {
     __shared__ float red[32];
     if (threadIdx.x < n_ranks) sys_wait_flag(my_flags + threadIdx.x, epoch);   // flags[0][src]: partial rows landed
     __syncthreads();
@@ -489,7 +521,7 @@ ep_reduce_norm_gather_kernel(const __nv_bfloat16* __restrict__ rs_buf, const int
                 for (int j = 0; j < 8; ++j) f[j] = f[j] * inv * g[j];
                 xo = pack8(f);
             }
-            for (int r = 0; r < n_ranks; ++r) {
+            for (int r = gather ? 0 : my_rank; r < (gather ? n_ranks : my_rank + 1); ++r) {
                 reinterpret_cast<uint4*>(peer_h[r] + tok * H)[idx] = v[i];
                 if (next_norm_w) reinterpret_cast<uint4*>(peer_xn[r] + tok * H)[idx] = xo;
             }
@@ -754,23 +786,48 @@ extern "C" int vita_ep_signal(void* const* peer_flags, int64_t which, int64_t n_
     return check_launch("ep_signal");
 }
 
-extern "C" int vita_ep_wait(const int32_t* my_flags, int64_t which, int64_t n_ranks, int64_t epoch, void* stream) {
+extern "C" int vita_ep_push(void* const* peer_base, const int64_t* offsets, const int64_t* bytes, int64_t n_ranges,
+                            int64_t n_ranks, int64_t my_rank, void* stream) {
+    VITA_REQUIRE(n_ranges >= 0 && n_ranges <= 4 && n_ranks >= 1 && n_ranks <= 32, "at most 4 ranges, 32 ranks");
+    PushRanges r{};
+    long long total = 0;
+    for (int i = 0; i < n_ranges; ++i) {
+        VITA_REQUIRE(offsets[i] % 16 == 0 && bytes[i] % 4 == 0 && bytes[i] >= 0,
+                     "range offsets must be 16-byte aligned, sizes multiples of 4");
+        r.off[i] = offsets[i];
+        r.bytes[i] = bytes[i];
+        total += bytes[i];
+    }
+    r.n = static_cast<int>(n_ranges);
+    if (total == 0 || n_ranks == 1) return VITA_OK;
+    long long blocks = (total / 16 + 255) / 256 + 1;
+    const int cap = 2 * (num_sms() > 0 ? num_sms() : 148);
+    if (blocks > cap) blocks = cap;
+    ep_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<uint8_t* const*>(peer_base), r, (int)n_ranks, (int)my_rank);
+    return check_launch("ep_push");
+}
+
+extern "C" int vita_ep_wait(const int32_t* my_flags, int64_t which, int64_t n_ranks, int64_t n_wait, int64_t epoch,
+                            void* stream) {
     VITA_REQUIRE(n_ranks >= 1 && n_ranks <= 32, "n_ranks must be in [1, 32]");
-    ep_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(my_flags, (int)which, (int)n_ranks, (int)epoch);
+    VITA_REQUIRE(n_wait >= 0 && n_wait <= n_ranks, "n_wait must be in [0, n_ranks]");
+    ep_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(my_flags, (int)which, (int)n_ranks, (int)n_wait,
+                                                                    (int)epoch);
     return check_launch("ep_wait");
 }
 
 extern "C" int vita_ep_reduce_norm_gather(const void* rs_buf, const int32_t* my_flags, void* const* peer_h,
                                           void* const* peer_xn, const void* next_norm_w, int64_t tok0, int64_t n_owned,
                                           int64_t n_ranks, int64_t my_rank, int64_t epoch, int64_t H, float eps,
-                                          void* stream) {
+                                          int64_t gather, void* stream) {
     VITA_REQUIRE(H % 8 == 0 && H <= 8 * 2 * 256, "H must be a multiple of 8 and <= 4096");
     VITA_REQUIRE(n_ranks >= 1 && n_ranks <= 32, "n_ranks must be in [1, 32]");
     if (n_owned == 0) return VITA_OK;
     ep_reduce_norm_gather_kernel<256, 2><<<static_cast<unsigned>(n_owned), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         BF(rs_buf), my_flags, reinterpret_cast<__nv_bfloat16* const*>(peer_h),
         reinterpret_cast<__nv_bfloat16* const*>(peer_xn), BF(next_norm_w), (int)tok0, (int)n_ranks, (int)my_rank,
-        (int)epoch, (int)H, eps);
+        (int)epoch, (int)H, eps, gather ? 1 : 0);
     return check_launch("ep_reduce_norm_gather");
 }
 

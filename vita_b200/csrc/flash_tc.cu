@@ -28,6 +28,7 @@ struct FaParams {
     int Sq, Skv;
     const int* kv_lens;           // [B] valid keys per batch entry, or nullptr
     int causal;
+    int q_pos0;                   // causal: key position of query row 0 (rows of a sequence shard start later)
     float scale_log2;             // softmax scale * log2(e)
     int n_qblk;                   // number of 128-row query blocks
     int pair_heads;               // NQ == 2: 1 = tiles are heads (2y, 2y+1) at the same rows, 0 = rows (2x, 2x+1)
@@ -96,7 +97,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (kv_len < 0) kv_len = 0;
     int n_tiles = (kv_len + FA_BN - 1) / FA_BN;
     if (p.causal) {
-        const int lim = (q0[NQ - 1] + FA_BM + FA_BN - 1) / FA_BN;   // keys <= last row of the last tile
+        const int lim = (p.q_pos0 + q0[NQ - 1] + FA_BM + FA_BN - 1) / FA_BN;   // keys <= last row of the last tile
         if (n_tiles > lim) n_tiles = lim;
     }
 
@@ -142,9 +143,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // TMEM columns: S_t at t*128 (P_t aliases the first 64 of them), O_t at NQ*128 + t*DV
 
     // Two query tiles: 384 threads leave 168 registers per thread, short of the 128 scores a softmax thread keeps
-    // live; the control warpgroup hands its registers to the softmax groups.
+    // live; the control warpgroup hands its registers to the softmax groups.  The pool is what the CTA got at launch
+    // (384 x 168): 128 x (168 - 72) released = 2 x 128 x (216 - 168) claimed, exactly.
     if (warp >= 4 * NQ) {
-        if constexpr (NQ == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        if constexpr (NQ == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
       if (warp == 4 * NQ) {
         // ------------------------------------------------------------------------------------ TMA producer
         if (lane == 0) {
@@ -251,9 +253,9 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
             tmem_ld_wait();
             const int col0 = j * FA_BN;
-            const bool boundary = (col0 + FA_BN > kv_len) || (p.causal && col0 + FA_BN - 1 > my_q0);   // warp-uniform
+            const bool boundary = (col0 + FA_BN > kv_len) || (p.causal && col0 + FA_BN - 1 > p.q_pos0 + my_q0);   // warp-uniform
             if (boundary) {
-                const int lim = p.causal ? min(kv_len, row + 1) : kv_len;   // columns >= lim are masked
+                const int lim = p.causal ? min(kv_len, p.q_pos0 + row + 1) : kv_len;   // columns >= lim are masked
 #pragma unroll
                 for (int i = 0; i < 128; ++i)
                     if (col0 + i >= lim) v[i] = 0xff800000u;   // -inf
@@ -262,11 +264,13 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
             const float m_new = fmaxf(m_ref, mx * p.scale_log2);
-            if (__any_sync(0xffffffffu, m_new > m_ref + 8.0f)) {
-                // move the reference: rescale the row sum and the accumulator (rows of this warp only)
-                const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx(m_ref - m_new);
+            const bool grow = m_new > m_ref + 8.0f;
+            if (__any_sync(0xffffffffu, grow)) {
+                // move the reference of the rows that need it (the decision is per row, so a row's result does not
+                // depend on its warp neighbours): rescale the row sum and the accumulator
+                const float alpha = grow ? ex2_approx(m_ref - m_new) : 1.0f;
                 l *= alpha;
-                m_ref = m_new;
+                if (grow) m_ref = m_new;
                 if (j > 0) {
 #pragma unroll
                     for (int c = 0; c < DV / 32; ++c) {
@@ -398,8 +402,8 @@ using namespace vita;
 extern "C" int vita_attention_fwd(const void* q, const void* k, const void* v, void* o, const int64_t* q_strides,
                                   const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
                                   int64_t B, int64_t n_q_heads, int64_t n_kv_heads, int64_t Sq, int64_t Skv,
-                                  int64_t d_qk, int64_t d_v, const int32_t* kv_lens, int causal, float scale,
-                                  void* stream) {
+                                  int64_t d_qk, int64_t d_v, const int32_t* kv_lens, int causal, int64_t q_pos0,
+                                  float scale, void* stream) {
     VITA_REQUIRE(n_kv_heads > 0 && n_q_heads % n_kv_heads == 0, "n_q_heads must be a multiple of n_kv_heads");
     VITA_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "q/k/v/o must be 16-byte aligned");
     for (int i = 0; i < 3; ++i)
@@ -409,6 +413,7 @@ extern "C" int vita_attention_fwd(const void* q, const void* k, const void* v, v
     VITA_REQUIRE(B <= 65535 && n_q_heads <= 65535, "batch / head count exceed the grid limits");
     if (B == 0 || Sq == 0) return VITA_OK;
     VITA_REQUIRE(Skv > 0, "Skv must be positive");
+    VITA_REQUIRE(q_pos0 >= 0 && (causal || q_pos0 == 0), "q_pos0 is the causal offset of query row 0 (>= 0)");
     FaParams p{};
     p.o = static_cast<__nv_bfloat16*>(o);
     p.o_bs = o_strides[0]; p.o_ts = o_strides[1]; p.o_hs = o_strides[2];
@@ -417,6 +422,7 @@ extern "C" int vita_attention_fwd(const void* q, const void* k, const void* v, v
     p.Skv = static_cast<int>(Skv);
     p.kv_lens = kv_lens;
     p.causal = causal;
+    p.q_pos0 = static_cast<int>(q_pos0);
     p.scale_log2 = scale * 1.4426950408889634f;
     auto st = static_cast<cudaStream_t>(stream);
     const int Bi = static_cast<int>(B), Hq = static_cast<int>(n_q_heads), Hkv = static_cast<int>(n_kv_heads);

@@ -21,7 +21,9 @@ class PagedKVCache:
     """k/v per layer: [num_pages * page_size, n_kv_heads, head_dim] bf16; block_table [max_batch, pages_per_seq]."""
 
     def __init__(self, cfg: LLMConfig, max_batch: int, max_seq_len: int, device, page_size: int = 16,
-                 shuffle_pages: bool = False):
+                 shuffle_pages: bool = False, storage=None):
+        """`storage(layer, "k" | "v", shape) -> tensor` lets the owner place the pages (e.g. in NVLink symmetric memory
+        for the sequence-sharded expert-parallel prefill); default: ordinary device allocations."""
         self.page_size = page_size
         self.pages_per_seq = (max_seq_len + page_size - 1) // page_size
         self.max_seq_len = self.pages_per_seq * page_size
@@ -29,8 +31,10 @@ class PagedKVCache:
         n_pages = max_batch * self.pages_per_seq
         slots = n_pages * page_size
         shape = (slots, cfg.num_key_value_heads, cfg.head_dim)
-        self.k = [torch.zeros(shape, dtype=BF16, device=device) for _ in range(cfg.num_hidden_layers)]
-        self.v = [torch.zeros(shape, dtype=BF16, device=device) for _ in range(cfg.num_hidden_layers)]
+        if storage is None:
+            storage = lambda layer, which, shp: torch.zeros(shp, dtype=BF16, device=device)
+        self.k = [storage(l, "k", shape) for l in range(cfg.num_hidden_layers)]
+        self.v = [storage(l, "v", shape) for l in range(cfg.num_hidden_layers)]
         order = torch.randperm(n_pages, generator=torch.Generator().manual_seed(0)) if shuffle_pages \
             else torch.arange(n_pages)
         table = order.view(max_batch, self.pages_per_seq).to(torch.int32)
@@ -54,8 +58,27 @@ class MixtralDecoder:
         self.device = torch.device(device)
         self.max_batch = max_batch
         max_seq_len = max_seq_len or (cfg.tokenizer_model_max_length + max_new_tokens)
-        assert max_seq_len <= weights["rope"].shape[0], "rope table too short for max_seq_len"
-        self.cache = PagedKVCache(cfg, max_batch, max_seq_len, device, page_size, shuffle_pages)
+        if max_seq_len > cfg.max_position_embeddings:
+            raise ValueError(f"max_seq_len {max_seq_len} exceeds max_position_embeddings {cfg.max_position_embeddings}")
+        page_rounded = (max_seq_len + page_size - 1) // page_size * page_size
+        if page_rounded > weights["rope"].shape[0]:      # cos/sin table sized from the KV capacity, not a constant
+            from ..weights import rope_table
+            weights["rope"] = rope_table(page_rounded, cfg.head_dim, cfg.rope_theta).to(self.device)
+        # expert parallelism: this rank holds experts [e_lo, e_hi) of every layer.  Modes (VITA_B200_EP):
+        #   seq  (default) sequence-sharded residual stream: every rank owns S/N tokens for the dense part (qkv, causal
+        #        attention over the all-gathered K/V, o-proj, router); K/V rows and routed activations are all-gathered
+        #        and the expert outputs pushed to the token owners by P2P stores over NVLink symmetric memory
+        #   p2p  replicated dense part, fused P2P combine (round-1 design, kept as the A/B baseline)
+        #   nccl replicated dense part, partial sums + NCCL all-reduce (library baseline)
+        self.ep_rank, self.ep_world = weights.get("ep", (0, 1))
+        self.ep_mode = os.environ.get("VITA_B200_EP", "seq") if self.ep_world > 1 else None
+        assert self.ep_mode in (None, "seq", "p2p", "nccl"), "VITA_B200_EP must be seq, p2p or nccl"
+        self.ep_p2p = None
+        storage = None
+        if self.ep_mode == "seq":
+            assert max_batch == 1 and not shuffle_pages, "sequence-sharded EP serves one sequence with in-order pages"
+            storage = self._init_ep_seq(page_rounded)
+        self.cache = PagedKVCache(cfg, max_batch, max_seq_len, device, page_size, shuffle_pages, storage)
         self.max_new_tokens = max_new_tokens
         self.decode_splits = int(os.environ.get("VITA_B200_ATTN_SPLITS", decode_splits))
         H, I = cfg.hidden_size, cfg.intermediate_size
@@ -88,20 +111,63 @@ class MixtralDecoder:
             self.mega = ops.MegaDecode(weights["layers"], weights["lm_head"], self.cache.k, self.cache.v, H, I,
                                        cfg.num_local_experts, cfg.num_attention_heads, cfg.num_key_value_heads,
                                        cfg.vocab_size, self.decode_splits, dev)
-        self._graph = None
-        self._graph_batch = None
+        self._graphs = {}             # single-sequence decode step: captured CUDA graph per (B, want_logits)
+        self.scores_buf = None        # [max_new_tokens + 1, V] logits log of slot 0 (generate(output_scores=True))
         self._bgraphs = {}            # batched decode step: captured CUDA graph per batch size
         self.d_slots = torch.zeros(B, dtype=torch.int32, device=dev)
         self._prefill_ws = {}
-        # expert parallelism: this rank holds experts [e_lo, e_hi) of every layer; attention, router, embeddings and
-        # the KV cache are replicated, the partial MoE outputs are summed with one all-reduce per layer
-        self.ep_rank, self.ep_world = weights.get("ep", (0, 1))
         per = cfg.num_local_experts // self.ep_world
         self.e_lo, self.e_hi = self.ep_rank * per, (self.ep_rank + 1) * per
         assert weights["layers"][0]["w13"].shape[0] == per, "expert tensors do not match the EP layout"
-        self.ep_p2p = None
-        if self.ep_world > 1 and os.environ.get("VITA_B200_EP", "p2p") == "p2p":
+        if self.ep_mode == "p2p":
             self._init_ep_p2p()
+
+    def _init_ep_seq(self, S_max: int):
+        """One NVLink symmetric allocation for the sequence-sharded expert-parallel prefill: receive slots of the
+        combine, residual stream / normed rows (own tokens), the all-gathered post-attention activations with their
+        routing records, epoch flags, and the K/V pages of every layer.  Returns the page-storage callback."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        c, N, dev = self.cfg, self.ep_world, self.device
+        H, L = c.hidden_size, c.num_hidden_layers
+        kv_row = c.num_key_value_heads * c.head_dim * 2                       # bytes of one K (or V) row
+        chunk_max = self.ep_chunk(S_max)
+        al = lambda n: (n + 255) // 256 * 256
+        names = ["rs", "h", "xn", "xn2", "ids", "tw", "flags", "kv"]
+        sizes = [al(chunk_max * 2 * H * 2), al(S_max * H * 2), al(S_max * H * 2), al(S_max * H * 2), al(S_max * 8),
+                 al(S_max * 8), al(4 * N * 4), 2 * L * al(S_max * kv_row)]
+        offs = [0]
+        for z in sizes:
+            offs.append(offs[-1] + z)
+        sym = symm_mem.empty(offs[-1], dtype=torch.uint8, device=dev)
+        sym.zero_()
+        torch.cuda.synchronize()
+        hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
+        delta = sym.data_ptr() - int(hdl.buffer_ptrs[hdl.rank])
+        bases = [int(p) + delta for p in hdl.buffer_ptrs]
+        assert hdl.world_size == N and hdl.rank == self.ep_rank
+        off = dict(zip(names, offs))
+        view = lambda n, dt: sym[off[n]:off[n] + sizes[names.index(n)]].view(dt)
+        ptrs = lambda n: torch.tensor([b + off[n] for b in bases], dtype=torch.int64, device=dev)
+        kv_layer = al(S_max * kv_row)
+        self.ep_p2p = dict(
+            sym=sym, hdl=hdl, chunk_max=chunk_max, off=off, kv_layer=kv_layer, kv_row=kv_row,
+            base_ptrs=torch.tensor(bases, dtype=torch.int64, device=dev),
+            rs=view("rs", BF16), h=view("h", BF16).view(S_max, H), xn=view("xn", BF16).view(S_max, H),
+            xn2=view("xn2", BF16).view(S_max, H), ids=view("ids", torch.int32).view(S_max, 2),
+            tw=view("tw", torch.float32).view(S_max, 2), flags=view("flags", torch.int32),
+            rs_ptrs=ptrs("rs"), h_ptrs=ptrs("h"), xn_ptrs=ptrs("xn"), flag_ptrs=ptrs("flags"), epoch=0)
+        dist.barrier()
+
+        def storage(layer, which, shape):
+            assert shape[0] == S_max, "K/V pages of the sequence-sharded prefill: one sequence, in-order pages"
+            o = off["kv"] + (2 * layer + (which == "v")) * kv_layer
+            return sym[o:o + S_max * kv_row].view(BF16).view(shape)
+        return storage
+
+    def ep_chunk(self, S: int) -> int:
+        """Tokens per rank of the sequence-sharded stream (multiple of 8: 16-byte aligned routing records)."""
+        return ((S + self.ep_world - 1) // self.ep_world + 7) // 8 * 8
 
     def _init_ep_p2p(self):
         """Symmetric (peer-mapped) buffers for the fused expert-parallel combine: every rank can store into every
@@ -140,25 +206,20 @@ class MixtralDecoder:
             cap = max(S, 2 * cap, 128)
             self._bgraphs = {}    # the batched-step graphs reference the old workspaces
             H, I, E, dev = c.hidden_size, c.intermediate_size, c.num_local_experts, self.device
-            self._prefill_ws = dict(
-                cap=cap,
-                xn=torch.empty(cap, H, dtype=BF16, device=dev),
-                qkv=torch.empty(cap, c.qkv_rows, dtype=BF16, device=dev),
-                attn=torch.empty(cap, c.num_attention_heads * c.head_dim, dtype=BF16, device=dev),
-                xn2=torch.empty(cap, H, dtype=BF16, device=dev),
-                ids=torch.empty(cap, 2, dtype=torch.int32, device=dev),
-                tw=torch.empty(cap, 2, dtype=torch.float32, device=dev),
-                offs=torch.empty(E + 1, dtype=torch.int32, device=dev),
-                perm=torch.empty(cap * 2, dtype=torch.int32, device=dev),
-                rtok=torch.empty(cap * 2, dtype=torch.int32, device=dev),
-                rw=torch.empty(cap * 2, dtype=torch.float32, device=dev),
-                xp=torch.empty(cap * 2, H, dtype=BF16, device=dev),
-                act=torch.empty(cap * 2, I, dtype=BF16, device=dev),
-                yp=torch.empty(cap * 2, H, dtype=BF16, device=dev),
-                ybuf=torch.empty(cap, H, dtype=BF16, device=dev) if self.ep_world > 1 else None,
-                rassign=torch.empty(cap * 2, dtype=torch.int32, device=dev),
-                pos=torch.arange(cap, dtype=torch.int32, device=dev))
+            with torch.inference_mode(False):      # reused across calls: keep them ordinary tensors
+                self._prefill_ws = self._alloc_ws(cap, H, I, E, dev)
         return self._prefill_ws
+
+    def _alloc_ws(self, cap, H, I, E, dev):
+        c = self.cfg
+        e = lambda *shape, dt=BF16: torch.empty(*shape, dtype=dt, device=dev)
+        return dict(
+            cap=cap, xn=e(cap, H), qkv=e(cap, c.qkv_rows), attn=e(cap, c.num_attention_heads * c.head_dim),
+            xn2=e(cap, H), ids=e(cap, 2, dt=torch.int32), tw=e(cap, 2, dt=torch.float32),
+            offs=e(E + 1, dt=torch.int32), perm=e(cap * 2, dt=torch.int32), rtok=e(cap * 2, dt=torch.int32),
+            rw=e(cap * 2, dt=torch.float32), xp=e(cap * 2, H), act=e(cap * 2, I), yp=e(cap * 2, H),
+            ybuf=e(cap, H) if self.ep_world > 1 else None, rassign=e(cap * 2, dt=torch.int32),
+            pos=torch.arange(cap, dtype=torch.int32, device=dev))
 
     @torch.no_grad()
     def prefill(self, inputs_embeds: torch.Tensor, slot: int = 0, all_logits: bool = False,
@@ -170,7 +231,10 @@ class MixtralDecoder:
         c, w = self.cfg, self.w
         S, H = inputs_embeds.shape
         assert inputs_embeds.dtype == BF16 and inputs_embeds.is_cuda and inputs_embeds.is_contiguous()
-        assert S <= self.cache.max_seq_len
+        if S > self.cache.max_seq_len:
+            raise ValueError(f"prompt of {S} tokens exceeds the KV capacity of {self.cache.max_seq_len} per sequence")
+        if self.ep_mode == "seq":
+            return self._prefill_ep_seq(inputs_embeds, slot, all_logits, want_last_logits)
         ws = self._ws(S)
         h = inputs_embeds
         p2p = self.ep_p2p
@@ -245,17 +309,98 @@ class MixtralDecoder:
             return ops.linear(xn, w["lm_head"])      # [S, V]; xn = final RMSNorm(h) written by the last combine
         return last_logits
 
+    @torch.no_grad()
+    def _prefill_ep_seq(self, inputs_embeds, slot, all_logits, want_last_logits):
+        """Sequence-sharded expert-parallel prefill (BASELINE configs[3]).  Rank r owns tokens
+        [t0, t1) for everything that is per-token (norms, qkv, o-proj, router, residual stream) and for their causal
+        attention over keys [0, t1); per layer three exchanges over NVLink peer memory, all by direct stores:
+          1. K/V rows of the own tokens -> every rank's pages (all-gather; a rank waits only for the ranks before it)
+          2. post-attention normed rows + routing records -> every rank (all-gather), so every rank can run the
+             grouped GEMMs of its local experts over the rows routed to them
+          3. the down-projection epilogue pushes each (token, k) output row to the token's owner (fused combine);
+             the owner sums its two slots into the residual stream and applies the next RMSNorm.
+        No partial sums anywhere: logits are bit-identical to the single-GPU model.  Returns the logits of the OWN rows
+        when `all_logits`, the last-row logits on the rank that owns the last token otherwise (None elsewhere)."""
+        assert slot == 0
+        c, w, sy = self.cfg, self.w, self.ep_p2p
+        S, H = inputs_embeds.shape
+        N, r = self.ep_world, self.ep_rank
+        chunk = self.ep_chunk(S)
+        t0, t1 = min(r * chunk, S), min((r + 1) * chunk, S)
+        n = t1 - t0
+        ws = self._ws(S)
+        nq, nkv, D, E = c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.num_local_experts
+        W = c.qkv_rows
+        h_own, xn_own = sy["h"][t0:t1], sy["xn"][t0:t1]
+        xn2, ids, tw = sy["xn2"][:S], sy["ids"][:S], sy["tw"][:S]
+        qkv, attn = ws["qkv"][:n], ws["attn"][:n]
+        perm, rtok, rw = ws["perm"][:2 * S], ws["rtok"][:2 * S], ws["rw"][:2 * S]
+        xp, act = ws["xp"][:2 * S], ws["act"][:2 * S]
+        pos, slots = ws["pos"][t0:t1], self.cache.slot_map[0, t0:t1]
+        off, kvl, kvr = sy["off"], sy["kv_layer"], sy["kv_row"]
+        offs_local = ws["offs"][self.e_lo:]
+        layers = w["layers"]
+        if n:
+            h_own.copy_(inputs_embeds[t0:t1])
+            ops.rmsnorm(h_own, layers[0]["ln1"], c.rms_norm_eps, out=xn_own)
+        for li, lw in enumerate(layers):
+            sy["epoch"] += 1
+            ep = sy["epoch"]
+            if n:
+                ops.linear(xn_own, lw["wqkv"], out=qkv)
+                ops.rope_kv_write(qkv, pos, slots, w["rope"], self.cache.k[li], self.cache.v[li], nq, nkv, D)
+                ko = off["kv"] + 2 * li * kvl + t0 * kvr
+                ops.ep_push(sy["base_ptrs"], [(ko, n * kvr), (ko + kvl, n * kvr)], N, r)
+            ops.ep_signal(sy["flag_ptrs"], 2, N, r, ep)
+            ops.ep_wait(sy["flags"], 2, N, ep, n_wait=r)          # K/V rows of the ranks before this one
+            if n:
+                ops.attention(qkv, self.cache.k[li], self.cache.v[li], attn, (0, W, D), (0, nkv * D, D),
+                              (0, nkv * D, D), (0, nq * D, D), 1, nq, nkv, n, t1, D, D, None, True, D ** -0.5,
+                              q_pos0=t0)
+                ops.linear(attn, lw["wo"], residual=h_own, out=h_own)
+                ops.moe_router(h_own, lw["ln2"], lw["gate"], xn2[t0:t1], ids[t0:t1], tw[t0:t1], c.rms_norm_eps)
+                ops.ep_push(sy["base_ptrs"], [(off["xn2"] + t0 * H * 2, n * H * 2), (off["ids"] + t0 * 8, n * 8),
+                                              (off["tw"] + t0 * 8, n * 8)], N, r)
+            ops.ep_signal(sy["flag_ptrs"], 3, N, r, ep)
+            ops.ep_wait(sy["flags"], 3, N, ep)
+            ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, S, E, row_assign=ws["rassign"][:2 * S])
+            ops.row_copy(xn2, rtok, None, xp, 2 * S)
+            ops.moe_gate_up(xp, lw["w13"], act, offs_local, 2 * S)
+            ops.moe_down_ep(act, lw["w2"], offs_local, rw, ws["rassign"][:2 * S], sy["rs_ptrs"], 2 * S, chunk)
+            ops.ep_signal(sy["flag_ptrs"], 0, N, r, ep)
+            nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else (w["norm"] if all_logits else None)
+            # (waits for flags[0] of every rank: all expert rows of the own tokens have landed)
+            ops.ep_reduce_norm_gather(sy["rs"], sy["flags"], sy["h_ptrs"], sy["xn_ptrs"], nxt, t0, n, N, r, ep, H,
+                                      c.rms_norm_eps, gather=False)
+            if n == 0:
+                ops.ep_wait(sy["flags"], 0, N, ep)   # keep the epochs of a token-less rank in step with the others
+        self.cache.cache_len[slot:slot + 1] += S
+        self.best[slot:slot + 1].zero_()
+        last_logits = None
+        if t0 <= S - 1 < t1:     # this rank owns the last token: first generated token
+            last_logits = self.d_logits[slot:slot + 1] if (want_last_logits or all_logits) else None
+            if self.use_tc:
+                ops.tc_lm_head_argmax(sy["h"][S - 1:S], H, w["norm"], w["lm_head"], last_logits,
+                                      self.best[slot:slot + 1], 1, self.tc_ws, c.rms_norm_eps)
+            else:
+                ops.lm_head_argmax(sy["h"][S - 1:S], H, w["norm"], w["lm_head"], last_logits,
+                                   self.best[slot:slot + 1], 1, c.rms_norm_eps)
+        if all_logits:
+            return ops.linear(xn_own, w["lm_head"]) if n else torch.empty(0, c.vocab_size, dtype=BF16, device=self.device)
+        return last_logits
+
     # ------------------------------------------------------------------------------------------ decode
     def _decode_step_kernels(self, B: int, want_logits: bool):
         c, w, cache = self.cfg, self.w, self.cache
         nq, nkv, D = c.num_attention_heads, c.num_key_value_heads, c.head_dim
         h = self.d_h[:B]
         ops.decode_embed(self.best[:B], self.token_log[:B], self.gen_count[:B], cache.cache_len[:B], cache.cur_pos[:B],
-                         w["embed"], h)
+                         w["embed"], h, cache.max_seq_len)
         if self.mega is not None and B == 1:
             self.mega.step(w["norm"], h, self.d_q[:1], self.d_attn[:1], self.d_act[:1],
                            self.d_logits[:1] if want_logits else None, self.best[:1], w["rope"], cache.cur_pos[:1],
                            cache.block_table[:1], cache.page_size, c.rms_norm_eps, D ** -0.5)
+            self._log_scores(B, want_logits)
             return
         tc, ws = self.use_tc, self.tc_ws
         l2pf = self.l2_prefetch
@@ -294,10 +439,29 @@ class MixtralDecoder:
             ops.tc_lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, ws, c.rms_norm_eps)
         else:
             ops.lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, c.rms_norm_eps)
+        self._log_scores(B, want_logits)
+
+    def enable_score_log(self):
+        """Allocate the per-step logits log (HF `output_scores=True`): row i holds the logits token i was chosen from.
+        The decode step appends to it on the device (row index = gen_count), so it works under CUDA-graph replay."""
+        if self.scores_buf is None:
+            with torch.inference_mode(False):   # persistent state must not become an inference tensor when the first
+                #                                 call happens under torch.inference_mode() (video_audio_demo.py:256)
+                self.scores_buf = torch.zeros(self.max_new_tokens + 1, self.cfg.vocab_size, dtype=BF16,
+                                              device=self.device)
+            self._graphs = {k: g for k, g in self._graphs.items() if not k[1]}   # re-capture the logits variants
+        return self.scores_buf
+
+    def _log_scores(self, B: int, want_logits: bool):
+        if want_logits and B == 1 and self.scores_buf is not None:
+            ops.row_copy(self.d_logits[:1], None, self.gen_count[:1], self.scores_buf, 1)
 
     @property
     def launches_per_decode_step(self) -> int:
         return 2 if self.mega is not None else 2 + 5 * self.cfg.num_hidden_layers
+
+    def launches_per_decode_step_with_scores(self) -> int:
+        return self.launches_per_decode_step + 1
 
     @torch.no_grad()
     def decode_step(self, B: int = 1, use_graph: bool = True, want_logits: bool = False):
@@ -311,7 +475,7 @@ class MixtralDecoder:
             self._decode_step_kernels(B, want_logits)
             return
         key = (B, want_logits)
-        if self._graph is None or self._graph_batch != key:
+        if key not in self._graphs:
             # capture (the kernels were warmed up by an eager step so every cudaFuncSetAttribute already ran)
             self._snapshot = self._save_state()
             self._decode_step_kernels(B, want_logits)
@@ -326,8 +490,8 @@ class MixtralDecoder:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self._restore_state(self._snapshot)   # capture does not execute, but keep the invariant explicit
-            self._graph, self._graph_batch = g, key
-        self._graph.replay()
+            self._graphs[key] = g
+        self._graphs[key].replay()
 
     # ------------------------------------------------------------------------------------------ batched decode
     def _batched_step_kernels(self, B: int, want_logits: bool):
@@ -339,7 +503,7 @@ class MixtralDecoder:
         ws = self._ws(max(B, 16))
         h = self.d_h[:B]
         ops.decode_embed(self.best[:B], self.token_log[:B], self.gen_count[:B], cache.cache_len[:B], cache.cur_pos[:B],
-                         w["embed"], h)
+                         w["embed"], h, cache.max_seq_len)
         slots = self.d_slots[:B]
         ops.decode_slots(cache.cur_pos[:B], cache.block_table[:B], slots, cache.page_size)
         xn, qkv, attn, xn2 = ws["xn"][:B], ws["qkv"][:B], ws["attn"][:B], ws["xn2"][:B]
@@ -402,6 +566,17 @@ class MixtralDecoder:
         self.best.copy_(s[0]); self.gen_count.copy_(s[1]); c.cache_len.copy_(s[2]); c.cur_pos.copy_(s[3])
         self.d_h.copy_(s[4]); self.token_log.copy_(s[5])
         # the KV slot written by the warm-up step is rewritten by the real step (same position): nothing to undo
+
+    def check_capacity(self, prompt_len: int, new_tokens: int):
+        """Every decode entry point calls this: prompt + reply must fit the paged KV cache of one sequence (the
+        kernels index block_table[pos / page_size] and the rope table without a bound of their own)."""
+        if prompt_len + new_tokens > self.cache.max_seq_len:
+            raise ValueError(f"prompt ({prompt_len}) + max_new_tokens ({new_tokens}) exceeds the KV capacity "
+                             f"({self.cache.max_seq_len} positions per sequence); build the model with a larger "
+                             f"max_seq_len")
+        if new_tokens > self.max_new_tokens:
+            raise ValueError(f"max_new_tokens {new_tokens} exceeds the token log ({self.max_new_tokens}); build the "
+                             f"model with a larger max_new_tokens")
 
     def reset(self):
         self.cache.reset()

@@ -220,6 +220,9 @@ class VITAMixtralForCausalLM:
     @torch.no_grad()
     def _embeds_for(self, input_ids, images, audios):
         if images is None or input_ids.shape[1] == 1:
+            if input_ids.shape[1] > self.llm.cache.max_seq_len:
+                raise ValueError(f"prompt of {input_ids.shape[1]} tokens exceeds the KV capacity "
+                                 f"{self.llm.cache.max_seq_len}")
             ids = input_ids.to(torch.int32).reshape(-1).to(self.device)
             out = torch.empty(ids.numel(), self.config.llm.hidden_size, dtype=BF16, device=self.device)
             ops.row_copy(self.packed["llm"]["embed"], ids, None, out, ids.numel())
@@ -236,6 +239,8 @@ class VITAMixtralForCausalLM:
         assert labels is None, "training is out of scope"
         if inputs_embeds is None and input_ids is not None and input_ids.shape[1] == 1 and past_key_values is not None:
             B = input_ids.shape[0]
+            if int(self.llm.cache.cache_len[:B].max()) + 1 > self.llm.cache.max_seq_len:
+                raise ValueError("the paged KV cache of this sequence is full (max_seq_len reached)")
             # teacher-forceable decode step: feed the given token (not necessarily the arg-max)
             packed = (0xFFFFFFFF - input_ids.reshape(-1).to(torch.int64)).to(self.device)
             self.llm.best[:B].copy_(packed)
@@ -268,10 +273,12 @@ class VITAMixtralForCausalLM:
         Returns the list of generated token lists.  `step_callback(step_index)` is called after every step launch
         (latency harnesses record CUDA events there)."""
         B = len(requests)
-        assert 1 <= B <= self.llm.max_batch and max_new_tokens <= self.llm.max_new_tokens
+        if not 1 <= B <= self.llm.max_batch:
+            raise ValueError(f"{B} requests do not fit max_batch = {self.llm.max_batch}")
         self.llm.reset()
         for b, r in enumerate(requests):
             emb, lens = self._embeds_for(r["input_ids"], r.get("images"), r.get("audios"))
+            self.llm.check_capacity(lens[0], max_new_tokens)
             self.llm.prefill(emb[0, : lens[0]].contiguous(), slot=b)
         for step in range(max_new_tokens):
             self.llm.decode_step_batched(B, use_graph=use_graph)
@@ -279,42 +286,97 @@ class VITAMixtralForCausalLM:
                 step_callback(step)
         return [self.llm.generated_tokens(b)[:max_new_tokens] for b in range(B)]
 
+    def prepare_inputs_for_generation_original(self, input_ids, past_key_values=None, attention_mask=None,
+                                               inputs_embeds=None, output_router_logits=False, **kwargs):
+        """vita_mixtral.py:291-352 (host-side bookkeeping of HF `generate`): keep only the tokens the KV cache has not
+        seen, derive position_ids from the mask.  `past_key_values` here is the opaque handle `forward` returns; the
+        number of cached tokens is the length of this object's paged cache (slot 0 ... B-1 advance together)."""
+        if past_key_values is not None:
+            past_length = int(self.llm.cache.cache_len[0])
+            if attention_mask is not None and attention_mask.shape[1] > input_ids.shape[1]:       # :311-312
+                input_ids = input_ids[:, -(attention_mask.shape[1] - past_length):]
+            elif past_length < input_ids.shape[1]:                                                # :315-316
+                input_ids = input_ids[:, past_length:]
+            else:                                                                                 # :318-320
+                input_ids = input_ids[:, input_ids.shape[1] - 1:]
+        position_ids = kwargs.get("position_ids", None)
+        if attention_mask is not None and position_ids is None:                                   # :330-335
+            position_ids = attention_mask.long().cumsum(-1) - 1
+            position_ids.masked_fill_(attention_mask == 0, 1)
+            if past_key_values:
+                position_ids = position_ids[:, -input_ids.shape[1]:]
+        if inputs_embeds is not None and past_key_values is None:                                 # :338-341
+            model_inputs = {"inputs_embeds": inputs_embeds}
+        else:
+            model_inputs = {"input_ids": input_ids}
+        model_inputs.update({"position_ids": position_ids, "past_key_values": past_key_values,
+                             "use_cache": kwargs.get("use_cache"), "attention_mask": attention_mask,
+                             "output_router_logits": output_router_logits})
+        return model_inputs
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, attention_mask=None,
+                                      output_router_logits=False, **kwargs):
+        """vita_mixtral.py:354-382: the original bookkeeping + `images` / `audios` re-attached."""
+        images = kwargs.pop("images", None)
+        audios = kwargs.pop("audios", None)
+        _inputs = self.prepare_inputs_for_generation_original(
+            input_ids, past_key_values=past_key_values, inputs_embeds=inputs_embeds, attention_mask=attention_mask,
+            output_router_logits=output_router_logits, **kwargs)
+        if images is not None:
+            _inputs["images"] = images
+        if audios is not None:
+            _inputs["audios"] = audios
+        return _inputs
+
     @torch.no_grad()
     def generate(self, input_ids, images=None, audios=None, do_sample=False, temperature=None, top_p=None,
                  num_beams=1, output_scores=False, return_dict_in_generate=True, max_new_tokens=16, use_cache=True,
                  stopping_criteria=None, eos_token_id: Optional[int] = None, use_graph: bool = True, sync_every: int = 16,
                  **kw):
-        """Greedy decode with the call signature of video_audio_demo.py:257-270.  `sequences` echoes the prompt ids
-        (placeholders included) followed by the new tokens (video_audio_demo.py:272-276)."""
-        assert not do_sample and num_beams == 1, "the hot path is greedy decode (do_sample=False, num_beams=1)"
-        assert input_ids.shape[0] == 1, "generate() is single-sequence like the demo; use the batched engine for more"
-        assert max_new_tokens <= self.llm.max_new_tokens
+        """Greedy decode with the call signature of video_audio_demo.py:257-270.  `sequences` (on `input_ids.device`)
+        echoes the prompt ids, placeholders included, followed by the new tokens (video_audio_demo.py:272-276).
+
+        The decode step replays as one CUDA graph whether or not `output_scores` is set: with scores the step appends
+        its logits row to a device-resident log, and `scores` are views of that log (valid until the next call).
+        Tokens are read back every `sync_every` steps; stopping criteria see each new token exactly once."""
+        if do_sample or num_beams != 1:
+            raise ValueError("the hot path is greedy decode (do_sample=False, num_beams=1)")
+        if input_ids.shape[0] != 1:
+            raise ValueError("generate() is single-sequence like the demo; use generate_batch() for more")
         emb, lens = self._embeds_for(input_ids, images, audios)
-        self.llm.reset()
-        first = self.llm.prefill(emb[0, : lens[0]].contiguous(), slot=0, want_last_logits=output_scores)
-        new_tokens: List[int] = []
-        scores = [first.clone()] if output_scores else []   # scores[i] are the logits token i was chosen from
+        llm = self.llm
+        llm.check_capacity(lens[0], max_new_tokens)
+        llm.reset()
+        score_log = llm.enable_score_log() if output_scores else None
+        first = llm.prefill(emb[0, : lens[0]].contiguous(), slot=0, want_last_logits=output_scores)
+        if output_scores:
+            score_log[0].copy_(first[0])
+        prompt = input_ids[0].tolist()
+        L = len(prompt)
+        seq_host = torch.empty(1, L + max_new_tokens, dtype=torch.long)      # one buffer; criteria get prefix views
+        seq_host[0, :L] = torch.tensor(prompt, dtype=torch.long)
+        n_new = checked = step = 0
         done = False
-        step = 0
         while step < max_new_tokens and not done:
             n = min(sync_every, max_new_tokens - step)
             for _ in range(n):
-                self.llm.decode_step(1, use_graph=use_graph and not output_scores, want_logits=output_scores)
-                if output_scores:
-                    scores.append(self.llm.d_logits[:1].clone())
+                llm.decode_step(1, use_graph=use_graph, want_logits=output_scores)
             step += n
-            toks = self.llm.generated_tokens(0)           # one host sync per `sync_every` tokens
-            new_tokens = toks[:max_new_tokens]
-            for i, t in enumerate(new_tokens):
-                stop = (eos_token_id is not None and t == eos_token_id)
+            toks = llm.generated_tokens(0)[:max_new_tokens]     # one host sync per `sync_every` tokens
+            n_new = len(toks)
+            seq_host[0, L + checked: L + n_new] = torch.tensor(toks[checked:], dtype=torch.long)
+            for i in range(checked, n_new):                     # only the tokens added since the last sync
+                stop = eos_token_id is not None and toks[i] == eos_token_id
                 if not stop and stopping_criteria:
-                    seq = torch.tensor([input_ids[0].tolist() + new_tokens[: i + 1]])
-                    stop = any(bool(sc(seq, None)) for sc in stopping_criteria)
+                    view = seq_host[:, : L + i + 1]
+                    stop = any(bool(sc(view, None)) for sc in stopping_criteria)
                 if stop:
-                    new_tokens = new_tokens[: i + 1]
+                    n_new = i + 1
                     done = True
                     break
-        seq = torch.tensor([input_ids[0].tolist() + new_tokens], dtype=torch.long)
+            checked = n_new
+        seq = seq_host[:, : L + n_new].to(input_ids.device)
         if not return_dict_in_generate:
             return seq
-        return GenerateOutput(seq, tuple(scores[: len(new_tokens)]) if output_scores else None)
+        scores = tuple(score_log[i: i + 1] for i in range(n_new)) if output_scores else None
+        return GenerateOutput(seq, scores)

@@ -106,15 +106,16 @@ def rope_kv_write(qkv: torch.Tensor, positions: torch.Tensor, slot_mapping: Opti
 
 # ------------------------------------------------------------------------------------------------ attention
 def attention(q, k, v, out, q_strides, k_strides, v_strides, o_strides, B, n_q, n_kv, Sq, Skv, d_qk, d_v,
-              kv_lens: Optional[torch.Tensor], causal: bool, scale: float) -> torch.Tensor:
-    """q/k/v/out: bf16 CUDA tensors (views allowed); *_strides = (batch, token, head) in elements."""
+              kv_lens: Optional[torch.Tensor], causal: bool, scale: float, q_pos0: int = 0) -> torch.Tensor:
+    """q/k/v/out: bf16 CUDA tensors (views allowed); *_strides = (batch, token, head) in elements.  causal: query
+    row i attends keys <= q_pos0 + i."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _chk(t, BF16, n, contiguous=False)
     if kv_lens is not None:
         _chk(kv_lens, torch.int32, "kv_lens")
     _lib.call("vita_attention_fwd", _p(q), _p(k), _p(v), _p(out), _i64arr(q_strides), _i64arr(k_strides),
               _i64arr(v_strides), _i64arr(o_strides), B, n_q, n_kv, Sq, Skv, d_qk, d_v, _p(kv_lens), int(causal),
-              float(scale), _stream())
+              int(q_pos0), float(scale), _stream())
     return out
 
 
@@ -179,14 +180,21 @@ def ep_signal(peer_flag_ptrs, which, n_ranks, my_rank, epoch):
     _lib.call("vita_ep_signal", _p(peer_flag_ptrs), which, n_ranks, my_rank, epoch, _stream())
 
 
-def ep_wait(my_flags, which, n_ranks, epoch):
-    _lib.call("vita_ep_wait", _p(my_flags), which, n_ranks, epoch, _stream())
+def ep_wait(my_flags, which, n_ranks, epoch, n_wait: Optional[int] = None):
+    _lib.call("vita_ep_wait", _p(my_flags), which, n_ranks, n_ranks if n_wait is None else n_wait, epoch, _stream())
+
+
+def ep_push(peer_base_ptrs, ranges, n_ranks, my_rank):
+    """All-gather by P2P stores: `ranges` = [(byte offset, bytes), ...] (<= 4) of this rank's symmetric buffer."""
+    offs = _i64arr([r[0] for r in ranges])
+    nbytes = _i64arr([r[1] for r in ranges])
+    _lib.call("vita_ep_push", _p(peer_base_ptrs), offs, nbytes, len(ranges), n_ranks, my_rank, _stream())
 
 
 def ep_reduce_norm_gather(rs_buf, my_flags, peer_h_ptrs, peer_xn_ptrs, next_norm_w, tok0, n_owned, n_ranks, my_rank,
-                          epoch, H, eps):
+                          epoch, H, eps, gather: bool = True):
     _lib.call("vita_ep_reduce_norm_gather", _p(rs_buf), _p(my_flags), _p(peer_h_ptrs), _p(peer_xn_ptrs),
-              _p(next_norm_w), tok0, n_owned, n_ranks, my_rank, epoch, H, float(eps), _stream())
+              _p(next_norm_w), tok0, n_owned, n_ranks, my_rank, epoch, H, float(eps), int(gather), _stream())
 
 
 def moe_gate_up(x_perm, w_gate_up, act, expert_offsets, rows):
@@ -291,11 +299,11 @@ def whale_adapter_im2col(x, lengths, out, B, T, C, ksize):
 
 
 # ------------------------------------------------------------------------------------------------ decode step
-def decode_embed(best, token_log, gen_count, cache_len, cur_pos, embed, h):
+def decode_embed(best, token_log, gen_count, cache_len, cur_pos, embed, h, max_ctx: int):
     _chk(best, torch.int64, "best"); _chk(token_log, torch.int32, "token_log"); _chk(embed, BF16, "embed")
     B, H = h.shape
     _lib.call("vita_decode_embed", _p(best), _p(token_log), _p(gen_count), token_log.shape[1], _p(cache_len),
-              _p(cur_pos), _p(embed), _p(h), B, H, embed.shape[0], _stream())
+              _p(cur_pos), _p(embed), _p(h), B, H, embed.shape[0], int(max_ctx), _stream())
 
 
 def decode_qkv_rope(h, norm_w, w_qkv, cos_sin, cur_pos, block_table, q_out, k_cache, v_cache, n_q, n_kv, head_dim,

@@ -178,6 +178,12 @@ def rope_table(max_pos: int, head_dim: int, theta: float) -> torch.Tensor:
     return torch.stack([freqs.cos(), freqs.sin()], dim=1).contiguous()
 
 
+def default_rope_len(c) -> int:
+    """Positions covered by the packed cos/sin table: the prompt limit plus room for the reply; the decoder grows the
+    table when it is built with a longer max_seq_len (MixtralDecoder.__init__)."""
+    return min(c.max_position_embeddings, max(c.tokenizer_model_max_length + 1024, 2048))
+
+
 def pack_llm(state, cfg: VitaConfig, device, ep=None) -> dict:
     c = cfg.llm
     e_lo, e_hi = (0, c.num_local_experts) if ep is None else expert_range(c.num_local_experts, ep[0], ep[1])
@@ -202,7 +208,7 @@ def pack_llm(state, cfg: VitaConfig, device, ep=None) -> dict:
             "ln2": dev(state[p + "post_attention_layernorm.weight"]),
             "gate": dev(state[p + moe + "gate.weight"]),
             "w13": dev(w13), "w2": dev(w2)})
-    out["rope"] = rope_table(min(c.max_position_embeddings, max(c.tokenizer_model_max_length + 1024, 2048)),
+    out["rope"] = rope_table(default_rope_len(c),
                              c.head_dim, c.rope_theta).to(device)
     out["ep"] = (0, 1) if ep is None else tuple(ep)
     return out
@@ -370,7 +376,7 @@ def random_packed(cfg: VitaConfig, device, seed: int = 0, parts=("llm", "vision"
                                     "b2": ((C,), "m")} for _ in range(a.num_blocks)]}
     fill(out, "w")
     if "llm" in out:
-        out["llm"]["rope"] = rope_table(min(c.max_position_embeddings, max(c.tokenizer_model_max_length + 1024, 2048)),
+        out["llm"]["rope"] = rope_table(default_rope_len(c),
                                         c.head_dim, c.rope_theta).to(device)
         out["llm"]["ep"] = (0, 1) if ep is None else tuple(ep)
     if "audio" in out:
