@@ -44,6 +44,15 @@ int64_t vita_launch_count(int reset);
 int vita_set_option(const char* name, int64_t value);
 int64_t vita_get_option(const char* name);
 
+/* Decode-chain completion counters (bs = 1 greedy step).  Between vita_chain_begin and vita_chain_end the chain-capable
+ * launches of the calling thread (vita_decode_tc_*, vita_decode_attention, vita_tc_lm_head_argmax) are linked in call
+ * order: each bumps its own 64-bit counter when its CTAs are done and polls its predecessor's instead of waiting for
+ * the grid dependency (which resolves ~3.5 us after the last CTA has exited).  mem = [1 + n_links] uint64, zeroed once
+ * (and again after a failed launch); mem[0] is the step serial that vita_decode_embed(..., serial = mem) bumps once per
+ * step.  Purely an accelerator: a counter that does not arrive in time falls back to the hardware dependency. */
+int vita_chain_begin(uint64_t* mem, int64_t n_links);
+int vita_chain_end(void);
+
 /* ---- dense linear:  C[M,N] = residual + colscale * act(A[M,K] . B[N,K]^T + bias) ----------------------------
  * tcgen05 / TMEM / TMA GEMM.  Replaces nn.Linear -> cuBLAS at
  *   internvit/modeling_intern_vit.py:180 (qkv), :192 (proj, with ls1 + residual :245-247),
@@ -197,10 +206,11 @@ int vita_whale_adapter_im2col(const void* x, const int32_t* lengths, void* out, 
 
 /* ---- greedy decode step (weight-streaming GEMVs) ---------------------------------------------------------- */
 /* consume the previous arg-max (best[b]), append it to token_log, advance cache_len, gather its embedding.
- * max_ctx = KV capacity per sequence (pages * page_size): cur_pos saturates at max_ctx - 1. */
+ * max_ctx = KV capacity per sequence (pages * page_size): cur_pos saturates at max_ctx - 1.
+ * chain_serial (may be NULL): step serial of the completion-counter chain, bumped once per call. */
 int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* gen_count, int64_t max_log, int32_t* cache_len,
                       int32_t* cur_pos, const void* embed, void* h, int64_t B, int64_t H, int64_t vocab,
-                      int64_t max_ctx, void* stream);
+                      int64_t max_ctx, uint64_t* chain_serial, void* stream);
 /* input_layernorm + fused q/k/v projection + RoPE + paged-KV append for one token per sequence. */
 int vita_decode_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, const float* cos_sin,
                          const int32_t* cur_pos, const int32_t* block_table, void* q_out, void* k_cache, void* v_cache,

@@ -71,3 +71,49 @@ def test_vision_tower_override_overlay(tiny_state, tmp_path):
     want.update({W.PREFIX_VISION + k: v for k, v in other.items()})
     assert set(merged) == set(want)
     _same(W.pack(merged, cfg, "cpu"), W.pack(want, cfg, "cpu"))
+
+
+def test_vllm_loader_name_map():
+    """vita_b200/vllm_adapter.py: names handed over by vLLM's loader -> checkpoint names (mixtral.py:1190-1229)."""
+    from vita_b200.vllm_adapter import MixtralForConditionalGeneration as M
+    assert M.checkpoint_name("language_model.model.layers.3.self_attn.q_proj.weight") == \
+        "model.layers.3.self_attn.q_proj.weight"
+    assert M.checkpoint_name("language_model.lm_head.weight") == "lm_head.weight"
+    assert M.checkpoint_name("model.layers.0.self_attn.rotary_emb.inv_freq") is None
+    assert M.checkpoint_name("model.vision_tower.vision_tower.embeddings.class_embedding") == \
+        "model.vision_tower.vision_tower.embeddings.class_embedding"
+
+
+def test_lora_adapter_is_merged_while_streaming(tiny_state, tmp_path):
+    """vita/model/builder.py:51-145 (`lora` in the model name + model_base): base weights + non_lora_trainables.bin +
+    the PEFT adapter merged as W + alpha / r * B @ A, tensor by tensor."""
+    from safetensors.torch import save_file
+    from vita_b200.model.builder import LazySafetensors, LoraMerged, _Overlay, _load_adapter, _non_lora_trainables
+    cfg, state = tiny_state
+    base, lora = tmp_path / "base", tmp_path / "vita-lora"
+    base.mkdir(); lora.mkdir()
+    save_file({k: v.contiguous() for k, v in state.items()}, str(base / "model.safetensors"))
+    g = torch.Generator().manual_seed(3)
+    r, alpha = 4, 8.0
+    targets = ["model.layers.0.self_attn.q_proj", "model.layers.1.block_sparse_moe.experts.2.w1", "lm_head"]
+    adapter = {}
+    for tname in targets:
+        out_f, in_f = state[tname + ".weight"].shape
+        adapter[f"base_model.model.{tname}.lora_A.weight"] = torch.randn(r, in_f, generator=g).bfloat16()
+        adapter[f"base_model.model.{tname}.lora_B.weight"] = torch.randn(out_f, r, generator=g).bfloat16() * 0.1
+    save_file(adapter, str(lora / "adapter_model.safetensors"))
+    (lora / "adapter_config.json").write_text(json.dumps({"r": r, "lora_alpha": alpha, "target_modules": ["q_proj", "w1"]}))
+    extra_name = "model.mm_projector.0.bias"
+    extra = {"base_model.model." + extra_name: torch.randn(state[extra_name].shape, generator=g).bfloat16()}
+    torch.save(extra, str(lora / "non_lora_trainables.bin"))
+
+    tensors, a, rr, rs = _load_adapter(lora)
+    merged = LoraMerged(_Overlay(_non_lora_trainables(lora), LazySafetensors(base)), tensors, a, rr, rs)
+    want = dict(state)
+    want[extra_name] = extra["base_model.model." + extra_name]
+    for tname in targets:
+        A, B = adapter[f"base_model.model.{tname}.lora_A.weight"], adapter[f"base_model.model.{tname}.lora_B.weight"]
+        want[tname + ".weight"] = (state[tname + ".weight"].float() + alpha / r * (B.float() @ A.float())).bfloat16()
+    assert set(merged) == set(want)
+    assert not torch.equal(merged["lm_head.weight"], state["lm_head.weight"])
+    _same(W.pack(merged, cfg, "cpu"), W.pack(want, cfg, "cpu"))

@@ -55,7 +55,9 @@ SIGNATURES = {
     "vita_whale_im2col2": (c_int, [P, P, I64, I64, I64, I64, P]),
     "vita_whale_qk_prep": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "vita_whale_adapter_im2col": (c_int, [P, P, P, I64, I64, I64, I64, P]),
-    "vita_decode_embed": (c_int, [P, P, P, I64, P, P, P, P, I64, I64, I64, I64, P]),
+    "vita_decode_embed": (c_int, [P, P, P, I64, P, P, P, P, I64, I64, I64, I64, P, P]),
+    "vita_chain_begin": (c_int, [P, I64]),
+    "vita_chain_end": (c_int, []),
     "vita_decode_qkv_rope": (c_int, [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, P]),
     "vita_decode_oproj": (c_int, [P, P, P, I64, I64, I64, P]),
     "vita_decode_router": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_float, P]),

@@ -65,6 +65,8 @@ static Option g_options[] = {
     // tcgen05 decode kernels: pull norm / router weights into L2 ahead of the dependency wait
     {"tc_prefetch_consts", "VITA_B200_TC_PREFETCH_CONSTS", 1, {-1}},
     // FlashAttention (flash_tc.cu): force the number of query tiles per CTA (0 = heuristic, 1, 2)
+    // decode chain: per-kernel completion counters polled by the successor instead of griddepcontrol.wait
+    {"chain_counters", "VITA_B200_CHAIN_COUNTERS", 1, {-1}},
     {"fa_nq", "VITA_B200_FA_NQ", 0, {-1}},
     // bring-up aids: override the MN-major V descriptor strides in bytes (0 = derived from the tile shape)
     {"fa_v_lbo", "VITA_B200_FA_V_LBO", 0, {-1}},
@@ -87,6 +89,29 @@ int option(const char* name) {
 }
 
 bool use_pdl() { return option("pdl") != 0; }
+
+// chain state of the calling host thread: set by vita_chain_begin, consumed link by link by the chain-capable launches
+struct ChainState {
+    unsigned long long* mem = nullptr;   // [0] = step serial, [1 + i] = counter of link i
+    long long n = 0, next = 0;
+    int prev_arrivals = 0;
+};
+static thread_local ChainState g_chain;
+
+ChainArgs chain_next(int arrivals) {
+    ChainArgs a{nullptr, nullptr, nullptr, 0};
+    ChainState& c = g_chain;
+    if (c.mem == nullptr || c.next >= c.n || !option("chain_counters")) return a;
+    a.serial = c.mem;
+    a.done_cnt = c.mem + 1 + c.next;
+    if (c.next > 0) {
+        a.wait_cnt = c.mem + c.next;
+        a.wait_arrivals = c.prev_arrivals;
+    }
+    c.prev_arrivals = arrivals;
+    ++c.next;
+    return a;
+}
 
 #ifdef VITA_TRACE
 static unsigned long long* g_trace_base = nullptr;
@@ -112,6 +137,19 @@ extern "C" int vita_set_option(const char* name, int64_t value) {
 }
 
 extern "C" int64_t vita_get_option(const char* name) { return name ? vita::option(name) : 0; }
+
+extern "C" int vita_chain_begin(uint64_t* mem, int64_t n_links) {
+    VITA_REQUIRE(mem != nullptr && n_links > 0, "vita_chain_begin: counter memory ([1 + n_links] x 8 bytes) required");
+    vita::g_chain.mem = reinterpret_cast<unsigned long long*>(mem);
+    vita::g_chain.n = n_links;
+    vita::g_chain.next = 0;
+    vita::g_chain.prev_arrivals = 0;
+    return VITA_OK;
+}
+extern "C" int vita_chain_end(void) {
+    vita::g_chain = vita::ChainState{};
+    return VITA_OK;
+}
 
 #ifdef VITA_TRACE
 // instrumentation builds only: records = number of 32-word records in buf; restarts the launch serial

@@ -69,7 +69,7 @@ __device__ __forceinline__ float attn_rescale(float m_old, float m_new) {
 //                 serial collector); lane groups are pre-merged with shuffles.
 template <bool TAGGED>
 __global__ void __launch_bounds__(128)
-decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
+decode_attn_kernel(const DecodeAttnParams p, const ChainArgsDev chain VITA_TRACE_PARAM) {
     __shared__ float s_m[16][DEC_GROUP];
     __shared__ float s_l[16][DEC_GROUP];
     __shared__ __align__(16) float s_o[TAGGED ? 4 : 16][DEC_GROUP][DEC_D];
@@ -82,7 +82,10 @@ decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
     if (threadIdx.x == 0 && split == 0) { VITA_STAMP(1); VITA_STAMP_SET(0, 2ull); }
 #endif
     pdl_launch_dependents();
-    if (!p.early) pdl_wait();
+    if (!p.early) {
+        if (threadIdx.x == 0) chain_wait(chain);
+        __syncthreads();
+    }
     // ---- before the dependency wait -------------------------------------------------------------------------------
     // cur_pos (first kernel of the step), the block table and every cached K/V row except the newest one are NOT
     // written by the kernel right before this one (the QKV projection of this layer), and the kernel before that has
@@ -123,7 +126,8 @@ decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
             pk[j][0] = pk[j][1] = pv[j][0] = pv[j][1] = make_uint4(0, 0, 0, 0);
         }
     }
-    pdl_wait();   // q and the newest K/V row come from the QKV kernel
+    if (threadIdx.x == 0) chain_wait(chain);   // q and the newest K/V row come from the QKV kernel
+    __syncthreads();
     if (threadIdx.x == 0 && split == 0) VITA_STAMP(3);
 #pragma unroll
     for (int j = 0; j < NPRE; ++j) {
@@ -325,6 +329,8 @@ decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
             p.out[(static_cast<long long>(b) * p.n_q + kvh * DEC_GROUP + oh) * DEC_D + od] =
                 __float2bfloat16(lt > 0.0f ? ot / lt : 0.0f);
         }
+        __syncthreads();                                  // the CTA's output stores are issued
+        if (threadIdx.x == 0) chain_arrive(chain);
         if (threadIdx.x == 0) VITA_STAMP(8);
         return;
     }
@@ -367,7 +373,10 @@ decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
         if (s_last) p.tickets[b * p.n_kv + kvh] = 0;
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) {
+        if (threadIdx.x == 0) chain_arrive(chain);
+        return;
+    }
     if (threadIdx.x == 0) VITA_STAMP(25);
     __threadfence();
     const long long sbase = (static_cast<long long>(b) * p.n_kv + kvh) * p.splits * DEC_GROUP;
@@ -405,6 +414,8 @@ decode_attn_kernel(const DecodeAttnParams p VITA_TRACE_PARAM) {
     }
     __syncthreads();   // every thread has read the (m, l) pairs
     if (d < p.splits * DEC_GROUP * 2) __stcg(&p.part_ml[sbase * 2 + d], 0.0f);
+    __syncthreads();
+    if (threadIdx.x == 0) chain_arrive(chain);
     if (threadIdx.x == 0) VITA_STAMP(8);
 }
 
@@ -457,9 +468,14 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
             carveout = want;
         }
     }
+    ChainArgsDev chain{nullptr, nullptr, nullptr, 0};
+    if (B == 1) {
+        const ChainArgs c = chain_next(static_cast<int>(splits * n_kv_heads));
+        chain = ChainArgsDev{c.serial, c.wait_cnt, c.done_cnt, c.wait_arrivals};
+    }
     cudaError_t e = tagged
-        ? launch_chain(decode_attn_kernel<true>, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p VITA_TRACE_ARG)
-        : launch_chain(decode_attn_kernel<false>, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p VITA_TRACE_ARG);
+        ? launch_chain(decode_attn_kernel<true>, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p, chain VITA_TRACE_ARG)
+        : launch_chain(decode_attn_kernel<false>, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p, chain VITA_TRACE_ARG);
     if (e != cudaSuccess) return check_cuda(e, "decode_attn_kernel");
     return check_launch("decode_attn_kernel");
 }

@@ -60,6 +60,19 @@ inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, s
 }
 
 
+// Decode-chain completion counters (an accelerator for the programmatic-launch chain, never needed for correctness):
+// every kernel of a bs = 1 decode step owns one monotonically increasing 64-bit counter that each of its CTAs bumps
+// after its last store; the successor polls it (target = step serial x arrivals per launch) instead of sitting in
+// griddepcontrol.wait, which returns ~3.5 us after the predecessor's last CTA has exited (grid teardown + flush).
+// A poll that does not succeed within a bounded number of tries falls back to griddepcontrol.wait.
+struct ChainArgs {
+    const unsigned long long* serial;     // step serial (bumped by decode_embed); nullptr = protocol off
+    const unsigned long long* wait_cnt;   // predecessor's counter, nullptr = first kernel of the chain
+    unsigned long long* done_cnt;         // this kernel's counter
+    int wait_arrivals;                    // arrivals per launch of the predecessor
+};
+ChainArgs chain_next(int arrivals);       // next link for a chain-capable launch (all-null when no chain is open)
+
 // Optional timeline instrumentation (build with -DVITA_TRACE): the decode-chain kernels stamp %globaltimer at a few
 // points into one 32-word record per launch; scripts/decode_trace.py turns the records into a per-kernel timeline.
 #ifdef VITA_TRACE

@@ -542,12 +542,14 @@ static int launch_stream_gemv(const Op& op, int x_elems, int B, cudaStream_t st,
 // Start of a decode step: consume the previous arg-max, log it, advance the cache length, gather the embedding.
 __global__ void __launch_bounds__(256)
 decode_embed_kernel(unsigned long long* best, int* token_log, int* gen_count, int max_log, int* cache_len,
-                    int* cur_pos, const __nv_bfloat16* embed, __nv_bfloat16* h, int H, int vocab, int max_ctx) {
+                    int* cur_pos, const __nv_bfloat16* embed, __nv_bfloat16* h, int H, int vocab, int max_ctx,
+                    unsigned long long* chain_serial) {
     const int b = blockIdx.x;
     __shared__ int s_tok;
     pdl_launch_dependents();
     pdl_wait();
     if (threadIdx.x == 0) {
+        if (b == 0 && chain_serial != nullptr) *chain_serial += 1;   // the step's kernels poll serial x arrivals
         const unsigned long long key = best[b];
         int tok = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull));
         if (tok < 0 || tok >= vocab) tok = 0;
@@ -697,14 +699,15 @@ extern "C" int vita_decode_slots(const int32_t* cur_pos, const int32_t* block_ta
 
 extern "C" int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* gen_count, int64_t max_log,
                                  int32_t* cache_len, int32_t* cur_pos, const void* embed, void* h, int64_t B,
-                                 int64_t H, int64_t vocab, int64_t max_ctx, void* stream) {
+                                 int64_t H, int64_t vocab, int64_t max_ctx, uint64_t* chain_serial, void* stream) {
     VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
     VITA_REQUIRE(max_ctx > 0 && max_ctx <= 0x7fffffff, "max_ctx (KV capacity per sequence) must be positive");
     if (B == 0) return VITA_OK;
     cudaError_t e = launch_chain(decode_embed_kernel, dim3(static_cast<unsigned>(B)), dim3(256), 0,
                                  static_cast<cudaStream_t>(stream), reinterpret_cast<unsigned long long*>(best),
                                  token_log, gen_count, (int)max_log, cache_len, cur_pos, BF16C(embed),
-                                 static_cast<__nv_bfloat16*>(h), (int)H, (int)vocab, (int)max_ctx);
+                                 static_cast<__nv_bfloat16*>(h), (int)H, (int)vocab, (int)max_ctx,
+                                 reinterpret_cast<unsigned long long*>(chain_serial));
     if (e != cudaSuccess) return check_cuda(e, "decode_embed");
     return check_launch("decode_embed");
 }

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 __global__ void __maxnreg__(Op::kMaxRegs)
 #endif
 tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned long long* __restrict__ g_scratch,
-               const int l2_ahead, const int flags VITA_TRACE_PARAM) {
+               const int l2_ahead, const int flags, const ChainArgsDev chain VITA_TRACE_PARAM) {
     constexpr int PARTS = Op::kParts, XPARTS = Op::kXParts, STAGES = Op::kStages;
     constexpr int STAGE_A = PARTS * TC_A_BYTES;
     constexpr int STAGE_X = XPARTS * TC_X_BYTES;
@@ -305,7 +305,8 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
     const bool wide = Op::kHasRoute && (flags & 8) != 0;
     if (wide) {
         if (warp >= 4) op.pre_wait(b, sm, (flags & 1) != 0);
-        pdl_wait();
+        if (threadIdx.x == 0) chain_wait(chain);
+        __syncthreads();
         op.wide_partials(b, sm);
         __syncthreads();
     }
@@ -314,7 +315,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer (weights)
             if (Op::kRowsNeedPrologue) mbar_wait(x_ready, 0, 21);      // expert ids computed by this CTA's prologue
-            else if (Op::kRowsNeedUpstream) pdl_wait();                 // expert ids written by the previous kernel
+            else if (Op::kRowsNeedUpstream) chain_wait(chain);          // expert ids written by the previous kernel
             int stage = 0;
             uint32_t phase = 0;
             // With programmatic dependent launch the next kernel of the chain may take the free half of the SM and fill
@@ -324,7 +325,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
             bool triggered = false;
             for (long long u = u0; u < u1; ++u) {
                 if (!triggered && u1 - u <= lead) {
-                    if ((flags & 2) && u > u0) pdl_wait();
+                    if ((flags & 2) && u > u0) chain_wait(chain);
                     pdl_launch_dependents();
                     triggered = true;
                 }
@@ -347,7 +348,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
                 }
             }
             if (!triggered) {
-                if (flags & 2) pdl_wait();
+                if (flags & 2) chain_wait(chain);
                 pdl_launch_dependents();
             }
             VITA_STAMP(6);
@@ -396,7 +397,8 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
         if constexpr (Op::kXFromGlobal) {
             // the vectors stay in L2; this warp keeps the chunks of the next LOOK units in registers
             constexpr int LOOK = 4;
-            pdl_wait();
+            if (lane == 0) chain_wait(chain);
+            __syncwarp();
             const __nv_bfloat16* xg = op.x_global(b);
             const int px = lane >> 3, c = lane & 7;
             const bool active = lane < 8 * XPARTS;
@@ -442,7 +444,8 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- prologue + epilogue (128 threads)
         if (!wide) op.pre_wait(b, sm, (flags & 1) != 0);   // constants only: L2 prefetch ahead of the dependency wait
-        pdl_wait();   // activations come from the previous kernel
+        if (threadIdx.x == 128) chain_wait(chain);   // activations come from the previous kernel
+        epi_barrier();
         if (threadIdx.x == 128) VITA_STAMP(3);
         op.prologue(b, sm, wide);
         epi_barrier();
@@ -550,6 +553,8 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
             u = seg_end;
         }
         op.finalize(b, st);
+        epi_barrier();                                   // every epilogue thread's stores are issued
+        if (threadIdx.x == 128) chain_arrive(chain);     // (the other warps of the CTA never write global memory)
         if (threadIdx.x == 128) VITA_STAMP(8);
     }
 
@@ -867,7 +872,12 @@ static int launch_tc(const Op& op, const void* W, long long w_rows, int K, int n
     const int flags = (option("tc_prefetch_consts") ? 1 : 0) | (option("chain_wait") ? 2 : 0) |
                       (option("tc_wide_route") ? 8 : 0) |
                       (option("tc_trigger_lead") << 8);
-    cudaError_t e = launch_chain(kern, grid, dim3(TC_THREADS), smem_bytes, st, tm, op, ws.scratch, l2_ahead, flags VITA_TRACE_ARG);
+    ChainArgsDev chain{nullptr, nullptr, nullptr, 0};
+    if (B == 1) {   // the counters protocol covers the bs = 1 step (fixed grids per chain position)
+        const ChainArgs c = chain_next(static_cast<int>(g));
+        chain = ChainArgsDev{c.serial, c.wait_cnt, c.done_cnt, c.wait_arrivals};
+    }
+    cudaError_t e = launch_chain(kern, grid, dim3(TC_THREADS), smem_bytes, st, tm, op, ws.scratch, l2_ahead, flags, chain VITA_TRACE_ARG);
     if (e != cudaSuccess) return check_cuda(e, name);
     return check_launch(name);
 }

@@ -207,6 +207,34 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---------------------------------------------------------------- decode-chain completion counters (see common.h)
+struct ChainArgsDev {
+    const unsigned long long* serial;
+    const unsigned long long* wait_cnt;
+    unsigned long long* done_cnt;
+    int wait_arrivals;
+};
+// one thread: returns once the predecessor's stores are visible (acquire); other threads follow through a CTA barrier
+__device__ __forceinline__ void chain_wait(const ChainArgsDev& c) {
+    if (c.wait_cnt != nullptr) {
+        const unsigned long long target = *reinterpret_cast<const volatile unsigned long long*>(c.serial) *
+                                          static_cast<unsigned long long>(c.wait_arrivals);
+        for (int i = 0; i < 4096; ++i) {
+            unsigned long long v;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(c.wait_cnt) : "memory");
+            if (v >= target) return;
+        }
+    }
+    pdl_wait();   // chain start, protocol off, or a counter that never arrived: the hardware dependency always holds
+}
+// one thread, after a CTA-level barrier that orders the CTA's last global stores before it
+__device__ __forceinline__ void chain_arrive(const ChainArgsDev& c) {
+    if (c.done_cnt != nullptr) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(c.done_cnt) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }

@@ -115,6 +115,68 @@ def _load_safetensors_dir(path: Path) -> LazySafetensors:
     return LazySafetensors(path)
 
 
+class LoraMerged:
+    """Read-only mapping that returns `W + (alpha / r) * B @ A` for every weight that has a LoRA pair in a PEFT adapter
+    and the base tensor otherwise -- what `PeftModel.from_pretrained(...).merge_and_unload()` leaves behind
+    (vita/model/builder.py:138-145), computed tensor by tensor while `weights.pack` streams the checkpoint, so the
+    merged model is never materialised on the host."""
+
+    def __init__(self, base, adapter: dict, lora_alpha: float, r: int, use_rslora: bool = False):
+        self.base = base
+        self.scale = lora_alpha / (r ** 0.5 if use_rslora else r)
+        self.pairs = {}
+        for k, a in adapter.items():
+            if ".lora_A." not in k:
+                continue
+            kb = k.replace(".lora_A.", ".lora_B.")
+            target = k.split(".lora_A.")[0]
+            for pre in ("base_model.model.", "base_model."):
+                if target.startswith(pre):
+                    target = target[len(pre):]
+                    break
+            self.pairs[target + ".weight"] = (a, adapter[kb])
+
+    def __contains__(self, key):
+        return key in self.base
+
+    def __iter__(self):
+        return iter(self.base)
+
+    def keys(self):
+        return self.base.keys() if hasattr(self.base, "keys") else list(self.base)
+
+    def __getitem__(self, key):
+        w = self.base[key]
+        pair = self.pairs.get(key)
+        if pair is None:
+            return w
+        a, b = pair
+        return (w.float() + self.scale * (b.float() @ a.float())).to(w.dtype)
+
+
+def _load_adapter(path: Path):
+    """PEFT adapter of a LoRA checkpoint directory: (tensors, lora_alpha, r, use_rslora)."""
+    cfg = json.loads((path / "adapter_config.json").read_text())
+    if (path / "adapter_model.safetensors").exists():
+        from safetensors.torch import load_file
+        tensors = load_file(str(path / "adapter_model.safetensors"))
+    else:
+        tensors = torch.load(str(path / "adapter_model.bin"), map_location="cpu")
+    return tensors, float(cfg["lora_alpha"]), int(cfg["r"]), bool(cfg.get("use_rslora", False))
+
+
+def _non_lora_trainables(path: Path) -> dict:
+    """vita/model/builder.py:108-137: extra full tensors saved next to the adapter, with the trainer's prefixes."""
+    f = path / "non_lora_trainables.bin"
+    if not f.exists():
+        return {}
+    t = torch.load(str(f), map_location="cpu")
+    t = {(k[11:] if k.startswith("base_model.") else k): v for k, v in t.items()}
+    if any(k.startswith("model.model.") for k in t):
+        t = {(k[6:] if k.startswith("model.") else k): v for k, v in t.items()}
+    return t
+
+
 def load_pretrained_model(model_path, model_base=None, model_name=None, model_type="mixtral-8x7b", load_8bit=False,
                           load_4bit=False, device_map="auto", device="cuda", **kwargs):
     """-> (tokenizer, model, image_processor, context_len), as vita/model/builder.py:306."""
@@ -132,13 +194,42 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, model_ty
         return None, VITAMixtralForCausalLM(cfg, packed, dev, **model_kwargs), None, cfg.llm.tokenizer_model_max_length
     path = Path(model_path)
     cfg = config_from_hf(json.loads((path / "config.json").read_text()))
-    state = _load_safetensors_dir(path)
+    is_lora = model_name is not None and "lora" in model_name.lower()
+    if is_lora and model_base is None:
+        import warnings                                                           # builder.py:47-50
+        warnings.warn("There is `lora` in model name but no `model_base` is provided. If you are loading a LoRA "
+                      "model, please provide the `model_base` argument.")
+    if is_lora and model_base is not None:
+        # builder.py:51-145: base weights, the non-LoRA trainables saved next to the adapter, then the merged adapter
+        base_dir = Path(model_base) if any(Path(model_base).glob("*.safetensors")) else path
+        state = _load_safetensors_dir(base_dir)
+        extra = _non_lora_trainables(path)
+        if extra:
+            state = _Overlay(extra, state)
+        adapter, alpha, r, rs = _load_adapter(path)
+        state = LoraMerged(state, adapter, alpha, r, rs)
+    elif model_base is not None:
+        # builder.py:146-176 ("this may be mm projector only"): language model from model_base, whatever tensors
+        # model_path holds (projector / encoders) on top
+        state = _load_safetensors_dir(Path(model_base))
+        if any(path.glob("*.safetensors")):
+            state = _Overlay(_load_safetensors_dir(path), state)
+        proj = path / "mm_projector.bin"
+        if proj.exists():
+            state = _Overlay(torch.load(str(proj), map_location="cpu"), state)
+    else:
+        state = _load_safetensors_dir(path)
     vt = kwargs.get("vision_tower_path")
     if vt:                                                                        # builder.py:245-257 override
         state = _Overlay(LazySafetensors(Path(vt), prefix=W.PREFIX_VISION), state)
     model = VITAMixtralForCausalLM(cfg, W.pack(state, cfg, dev), dev, **model_kwargs)
-    for s_ in (state.primary, state.base) if isinstance(state, _Overlay) else (state,):
-        s_.close()
+    def _close(m):
+        for part in (getattr(m, "primary", None), getattr(m, "base", None)):
+            if part is not None:
+                _close(part)
+        if hasattr(m, "close"):
+            m.close()
+    _close(state)
     tokenizer = image_processor = None
     try:
         from transformers import AutoTokenizer

@@ -111,6 +111,8 @@ class MixtralDecoder:
             self.mega = ops.MegaDecode(weights["layers"], weights["lm_head"], self.cache.k, self.cache.v, H, I,
                                        cfg.num_local_experts, cfg.num_attention_heads, cfg.num_key_value_heads,
                                        cfg.vocab_size, self.decode_splits, dev)
+        # completion counters of the bs = 1 decode chain: [serial, one counter per chain kernel (5 per layer + LM head)]
+        self.chain_mem = torch.zeros(2 + 5 * cfg.num_hidden_layers, dtype=torch.int64, device=dev)
         self._graphs = {}             # single-sequence decode step: captured CUDA graph per (B, want_logits)
         self.scores_buf = None        # [max_new_tokens + 1, V] logits log of slot 0 (generate(output_scores=True))
         self._bgraphs = {}            # batched decode step: captured CUDA graph per batch size
@@ -167,7 +169,8 @@ class MixtralDecoder:
 
     def ep_chunk(self, S: int) -> int:
         """Tokens per rank of the sequence-sharded stream (multiple of 8: 16-byte aligned routing records)."""
-        return ((S + self.ep_world - 1) // self.ep_world + 7) // 8 * 8
+        from ..parallel import sequence_chunk
+        return sequence_chunk(S, self.ep_world)
 
     def _init_ep_p2p(self):
         """Symmetric (peer-mapped) buffers for the fused expert-parallel combine: every rank can store into every
@@ -325,8 +328,9 @@ class MixtralDecoder:
         c, w, sy = self.cfg, self.w, self.ep_p2p
         S, H = inputs_embeds.shape
         N, r = self.ep_world, self.ep_rank
+        from ..parallel import token_range
         chunk = self.ep_chunk(S)
-        t0, t1 = min(r * chunk, S), min((r + 1) * chunk, S)
+        t0, t1 = token_range(S, r, N)
         n = t1 - t0
         ws = self._ws(S)
         nq, nkv, D, E = c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.num_local_experts
@@ -394,8 +398,20 @@ class MixtralDecoder:
         c, w, cache = self.cfg, self.w, self.cache
         nq, nkv, D = c.num_attention_heads, c.num_key_value_heads, c.head_dim
         h = self.d_h[:B]
+        chained = B == 1 and self.use_tc and self.mega is None and not self.l2_prefetch
         ops.decode_embed(self.best[:B], self.token_log[:B], self.gen_count[:B], cache.cache_len[:B], cache.cur_pos[:B],
-                         w["embed"], h, cache.max_seq_len)
+                         w["embed"], h, cache.max_seq_len, self.chain_mem if chained else None)
+        if chained:
+            ops.chain_begin(self.chain_mem)
+        try:
+            self._decode_layers(B, want_logits, h)
+        finally:
+            if chained:
+                ops.chain_end()
+
+    def _decode_layers(self, B: int, want_logits: bool, h):
+        c, w, cache = self.cfg, self.w, self.cache
+        nq, nkv, D = c.num_attention_heads, c.num_key_value_heads, c.head_dim
         if self.mega is not None and B == 1:
             self.mega.step(w["norm"], h, self.d_q[:1], self.d_attn[:1], self.d_act[:1],
                            self.d_logits[:1] if want_logits else None, self.best[:1], w["rope"], cache.cur_pos[:1],
@@ -580,6 +596,7 @@ class MixtralDecoder:
 
     def reset(self):
         self.cache.reset()
+        self.chain_mem.zero_()     # completion counters restart with the request (also heals an aborted step)
         self.best.zero_()
         self.gen_count.zero_()
         self.token_log.zero_()

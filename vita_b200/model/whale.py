@@ -28,6 +28,7 @@ class AudioEncoder:
         # (video_audio_demo.py:183-187); the filterbank itself runs on the GPU (csrc/fbank.cu)
         from ..audio_frontend import AudioProcessor
         self.audio_processor = AudioProcessor(device)
+        self._pos_proj = {}     # T2 -> per-layer linear_pos(pos_emb): input independent, computed once per length
 
     def to(self, *args, **kwargs):  # the demo calls audio_encoder.to(dtype=torch.float16) (video_audio_demo.py:176)
         return self
@@ -53,7 +54,10 @@ class AudioEncoder:
         x = ops.linear(x, w["embed_w"], w["embed_b"])
         x = ops.layernorm(x, w["embed_ln_w"], w["embed_ln_b"], c.layer_norm_eps, ops.ACT_RELU, math.sqrt(C))
         assert T2 < c.max_len
-        pos = w["pos_table"][:T2]
+        if T2 not in self._pos_proj:      # attention.py:381 p = linear_pos(pos_emb): depends on the length only
+            with torch.inference_mode(False):
+                self._pos_proj[T2] = [ops.linear(w["pos_table"][:T2], lw["pos_w"]) for lw in w["layers"]]
+        pos_proj = self._pos_proj[T2]
         nh, dk = c.num_attention_heads, c.head_dim
         y = torch.empty_like(x)
         qkv = torch.empty(B * T2, 3 * C, dtype=BF16, device=self.device)
@@ -61,10 +65,9 @@ class AudioEncoder:
         k2 = torch.empty_like(q2)
         attn = torch.empty_like(x)
         mid = torch.empty(B * T2, c.linear_units, dtype=BF16, device=self.device)
-        for lw in w["layers"]:
+        for lw, p in zip(w["layers"], pos_proj):
             ops.layernorm(x, lw["ln1_w"], lw["ln1_b"], c.layer_norm_eps, out=y)
             ops.linear(y, lw["qkv_w"], lw["qkv_b"], out=qkv)
-            p = ops.linear(pos, lw["pos_w"])
             ops.whale_qk_prep(qkv, p, lw["bias_u"], lw["bias_v"], q2, k2, B, T2, nh, dk)
             ops.attention(q2, k2, qkv[:, 2 * C:], attn, (T2 * nh * 2 * dk, nh * 2 * dk, 2 * dk),
                           (T2 * nh * 2 * dk, nh * 2 * dk, 2 * dk), (T2 * 3 * C, 3 * C, dk), (T2 * C, C, dk), B, nh, nh,

@@ -299,11 +299,22 @@ def whale_adapter_im2col(x, lengths, out, B, T, C, ksize):
 
 
 # ------------------------------------------------------------------------------------------------ decode step
-def decode_embed(best, token_log, gen_count, cache_len, cur_pos, embed, h, max_ctx: int):
+def decode_embed(best, token_log, gen_count, cache_len, cur_pos, embed, h, max_ctx: int,
+                 chain_mem: Optional[torch.Tensor] = None):
     _chk(best, torch.int64, "best"); _chk(token_log, torch.int32, "token_log"); _chk(embed, BF16, "embed")
     B, H = h.shape
     _lib.call("vita_decode_embed", _p(best), _p(token_log), _p(gen_count), token_log.shape[1], _p(cache_len),
-              _p(cur_pos), _p(embed), _p(h), B, H, embed.shape[0], int(max_ctx), _stream())
+              _p(cur_pos), _p(embed), _p(h), B, H, embed.shape[0], int(max_ctx), _p(chain_mem), _stream())
+
+
+def chain_begin(chain_mem: torch.Tensor):
+    """Open a completion-counter chain: chain_mem = int64 [1 + n_links] (serial + one counter per chain kernel)."""
+    _chk(chain_mem, torch.int64, "chain_mem")
+    _lib.call("vita_chain_begin", _p(chain_mem), chain_mem.numel() - 1)
+
+
+def chain_end():
+    _lib.call("vita_chain_end")
 
 
 def decode_qkv_rope(h, norm_w, w_qkv, cos_sin, cur_pos, block_table, q_out, k_cache, v_cache, n_q, n_kv, head_dim,

@@ -1,9 +1,12 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed for rendezvous and the few scalar reductions.
 
-The omni forward path shards by *request* (SURVEY.md section 8e "request-parallel"): the whole model (93.7 GB bf16) fits one
-180 GB B200, so each rank owns complete requests and their KV cache and the data path needs no collective.  The only
-exchanges are bookkeeping: max-over-ranks timings and gathering generated token lists on rank 0.
-(Expert-parallel all-to-all for one long sequence -- BASELINE configs[3] -- is DESIGN.md "next".)
+Two ways the omni forward path shards:
+* by *request* (decode, short prompts): the whole model (93.7 GB bf16) fits one 180 GB B200, so each rank owns
+  complete requests and their KV cache and the data path needs no collective; the only exchanges are bookkeeping
+  (max-over-ranks timings, gathering generated token lists on rank 0);
+* by *expert and token* (one long sequence, BASELINE configs[3]): rank r holds experts [r E/N, (r+1) E/N) and owns the
+  token chunk `token_range(S, r, N)` of the residual stream; `MixtralDecoder._prefill_ep_seq` moves K/V rows, routed
+  activations and expert outputs between ranks with P2P stores over NVLink symmetric memory.
 """
 from __future__ import annotations
 
@@ -29,6 +32,18 @@ def init(backend: str, device=None):
 def shard_requests(n_requests: int, rank: int, world: int) -> List[int]:
     """Round-robin request ownership: request i runs on rank i % world (balanced to within one request)."""
     return list(range(rank, n_requests, world))
+
+
+def sequence_chunk(S: int, world: int) -> int:
+    """Tokens per rank of a sequence-sharded residual stream: ceil(S / world) rounded up to a multiple of 8 (keeps the
+    8-byte routing records of a chunk 16-byte aligned for the P2P all-gather)."""
+    return ((S + world - 1) // world + 7) // 8 * 8
+
+
+def token_range(S: int, rank: int, world: int):
+    """[t0, t1) owned by `rank`; trailing ranks may own nothing when S is short."""
+    chunk = sequence_chunk(S, world)
+    return min(rank * chunk, S), min((rank + 1) * chunk, S)
 
 
 def reduce_max(x: float, device="cpu") -> float:
