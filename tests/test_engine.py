@@ -47,6 +47,9 @@ class FakeEngine:
     def read_tokens(self, slot):
         return self.log[slot, : int(self.count[slot])].tolist()
 
+    def first_token(self, slot):
+        return stream(int(self.seed[slot]), 1)[0]
+
 
 def expected(r: Request):
     toks = stream(r.payload["seed"], r.max_new_tokens)
@@ -95,3 +98,53 @@ def test_arrivals_fill_freed_slots_and_idle_gaps_are_skipped():
     # request 2 has to wait for request 1's slot; request 3 arrives long after everything finished
     assert reqs[2].admitted_step == 2 and reqs[3].admitted_step == 100
     assert eng.steps == 5 + 2        # steps 0..4 for the first three, then 2 for the late arrival (no idle steps)
+
+
+def test_duplex_negative_query_is_dropped_after_prefill():
+    """web_interactive_demo.py:251-253,368-370: a reply that starts with the `<2>` state token is abandoned at once."""
+    neg = stream(77, 1)[0]
+    reqs = [Request(0, {"seed": 5}, 6, None, 0, session=1, negative_token_id=neg),
+            Request(1, {"seed": 77}, 6, None, 2, session=1, negative_token_id=neg),     # noise while request 0 talks
+            Request(2, {"seed": 9}, 4, None, 3, session=2, negative_token_id=neg)]
+    eng = FakeEngine(4, cap=16)
+    out = ContinuousBatcher(eng, 4).run(reqs)
+    assert out[1] == [neg] and reqs[1].outcome == "negative" and reqs[1].finished_step == reqs[1].admitted_step
+    # the noise query neither interrupted request 0 nor took a decode slot
+    assert out[0] == stream(5, 6) and reqs[0].outcome == "finished"
+    assert out[2] == stream(9, 4) and eng.max_active == 2
+
+
+def test_duplex_real_query_interrupts_the_running_answer_of_its_session():
+    """web_interactive_demo.py:340-353: the first non-negative token of a new query stops the other answer."""
+    reqs = [Request(0, {"seed": 5}, 20, None, 0, session=1, negative_token_id=-1),
+            Request(1, {"seed": 6}, 20, None, 0, session=2, negative_token_id=-1),       # another conversation
+            Request(2, {"seed": 7}, 5, None, 4, session=1, negative_token_id=-1)]       # barge-in at step 4
+    eng = FakeEngine(4, cap=32)
+    out = ContinuousBatcher(eng, 4).run(reqs)
+    assert reqs[0].outcome == "interrupted" and out[0] == stream(5, 4)      # 4 tokens were produced before the barge-in
+    assert reqs[0].finished_step == 4 == reqs[2].admitted_step
+    assert out[1] == stream(6, 20) and reqs[1].outcome == "finished"        # the other session is untouched
+    assert out[2] == stream(7, 5) and reqs[2].outcome == "finished"
+    assert eng.max_active == 2
+
+
+@pytest.mark.parametrize("trial", range(4))
+def test_duplex_random_sessions_keep_streams_intact(trial):
+    rng = random.Random(100 + trial)
+    reqs, t = [], 0
+    for rid in range(30):
+        t += rng.randint(0, 6)
+        seed = rng.randint(1, 10 ** 6)
+        reqs.append(Request(rid, {"seed": seed}, rng.randint(1, 12), None, t, session=rng.randint(0, 3),
+                            negative_token_id=stream(seed, 1)[0] if rng.random() < 0.3 else -1))
+    eng = FakeEngine(4, cap=40)
+    out = ContinuousBatcher(eng, 4, sync_every=rng.choice([1, 2])).run(reqs)
+    assert set(out) == {r.rid for r in reqs}
+    for r in reqs:
+        full = stream(r.payload["seed"], r.max_new_tokens)
+        if r.outcome == "negative":
+            assert out[r.rid] == full[:1]
+        elif r.outcome == "interrupted":
+            assert out[r.rid] == full[: len(out[r.rid])] and len(out[r.rid]) <= r.max_new_tokens
+        else:
+            assert out[r.rid] == full
