@@ -512,46 +512,33 @@ def run_b200(args):
 
     # ---- dominant kernel ------------------------------------------------------------------------------------
     c = cfg.llm
-    if llm.mega is not None:
-        # single-kernel decode step: the dominant kernel IS the step; its duration comes from the timed region
-        roof_kernel = ("decode_mega_kernel (one persistent launch per token: all 32 layers' tcgen05 GEMVs, paged "
-                       "attention, router, LM head + arg-max)")
-        gu_ms = dec_ms / NT
-        gu_bytes = decode_bytes(S + NT // 2, cfg)
-        roof_note = "duration = decode time per token inside the timed region (CUDA events around the graph replays)"
-    else:
-        # per-kernel path: the expert gate/up GEMV (60% of the decode bytes), timed with CUDA events on the launching
-        # stream in an eager pass right after the timed region (inside it the step is one CUDA graph)
-        lw = packed["llm"]["layers"]
+    # the expert gate/up GEMV (60% of the decode bytes), timed with CUDA events on the launching stream in an eager
+    # pass right after the timed region (inside it the step is one CUDA graph)
+    lw = packed["llm"]["layers"]
 
-        def launch_all():
-            for li in range(len(lw)):
-                if llm.use_tc:
-                    ops.decode_tc_moe_gate_up(llm.d_h[:1], lw[li]["ln2"], lw[li]["gate"], lw[li]["w13"], llm.d_ids[:1],
-                                              llm.d_w[:1], llm.d_act[:1], llm.tc_ws, c.rms_norm_eps)
-                else:
-                    ops.decode_moe_gate_up(llm.d_h[:1], lw[li]["ln2"], lw[li]["gate"], lw[li]["w13"], llm.d_ids[:1],
-                                           llm.d_w[:1], llm.d_act[:1], c.rms_norm_eps)
+    def launch_all():
+        for li in range(len(lw)):
+            ops.decode_tc_moe_gate_up(llm.d_h[:1], lw[li]["ln2"], lw[li]["gate"], lw[li]["w13"], llm.d_ids[:1],
+                                      llm.d_w[:1], llm.d_act[:1], llm.tc_ws, c.rms_norm_eps)
 
-        # one launch per layer (32 different 470 MB weight sets, far larger than L2), back to back on the stream;
-        # average duration = elapsed / launches
+    # one launch per layer (32 different 470 MB weight sets, far larger than L2), back to back on the stream;
+    # average duration = elapsed / launches
+    launch_all()
+    torch.cuda.synchronize()
+    reps, gu_ms = 3, 0.0
+    for r in range(reps):
+        a, b = ev(), ev()
+        a.record()
         launch_all()
-        torch.cuda.synchronize()
-        reps, gu_ms = 3, 0.0
-        for r in range(reps):
-            a, b = ev(), ev()
-            a.record()
-            launch_all()
-            b.record()
-            b.synchronize()
-            gu_ms += a.elapsed_time(b)
-        gu_ms /= reps * len(lw)
-        gu_bytes = c.num_experts_per_tok * 2 * c.intermediate_size * c.hidden_size * 2 + c.hidden_size * 2 \
-            + c.num_experts_per_tok * c.intermediate_size * 2 + c.num_local_experts * c.hidden_size * 2
-        roof_kernel = ("tc_gemv_kernel<TcGateUpOp>" if llm.use_tc else "stream_gemv_kernel<GateUpOp>") + \
-            " (decode: fused RMSNorm + router + the 2 selected experts' gate/up rows + SiLU*up)"
-        roof_note = ("one launch per layer back to back on the stream, CUDA events around the batch, right after the timed "
-                     "region (inside it the decode step is a single CUDA graph)")
+        b.record()
+        b.synchronize()
+        gu_ms += a.elapsed_time(b)
+    gu_ms /= reps * len(lw)
+    gu_bytes = c.num_experts_per_tok * 2 * c.intermediate_size * c.hidden_size * 2 + c.hidden_size * 2 \
+        + c.num_experts_per_tok * c.intermediate_size * 2 + c.num_local_experts * c.hidden_size * 2
+    roof_kernel = "tc_gemv_kernel<TcGateUpOp> (decode: fused RMSNorm + router + the 2 selected experts' gate/up rows + SiLU*up)"
+    roof_note = ("one launch per layer back to back on the stream, CUDA events around the batch, right after the timed "
+                 "region (inside it the decode step is a single CUDA graph)")
     pk = peaks()
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------------------

@@ -204,46 +204,23 @@ int vita_whale_qk_prep(const void* qkv, const void* p, const void* bias_u, const
 int vita_whale_adapter_im2col(const void* x, const int32_t* lengths, void* out, int64_t B, int64_t T, int64_t C,
                               int64_t ksize, void* stream);
 
-/* ---- greedy decode step (weight-streaming GEMVs) ---------------------------------------------------------- */
+/* ---- greedy decode step: small kernels --------------------------------------------------------------------- */
 /* consume the previous arg-max (best[b]), append it to token_log, advance cache_len, gather its embedding.
  * max_ctx = KV capacity per sequence (pages * page_size): cur_pos saturates at max_ctx - 1.
  * chain_serial (may be NULL): step serial of the completion-counter chain, bumped once per call. */
 int vita_decode_embed(uint64_t* best, int32_t* token_log, int32_t* gen_count, int64_t max_log, int32_t* cache_len,
                       int32_t* cur_pos, const void* embed, void* h, int64_t B, int64_t H, int64_t vocab,
                       int64_t max_ctx, uint64_t* chain_serial, void* stream);
-/* input_layernorm + fused q/k/v projection + RoPE + paged-KV append for one token per sequence. */
-int vita_decode_qkv_rope(const void* h, const void* norm_w, const void* w_qkv, const float* cos_sin,
-                         const int32_t* cur_pos, const int32_t* block_table, void* q_out, void* k_cache, void* v_cache,
-                         int64_t B, int64_t H, int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim,
-                         int64_t page_size, int64_t max_pages, float eps, void* stream);
-/* h += x . W^T (o_proj + residual). */
-int vita_decode_oproj(const void* x, const void* w, void* h, int64_t B, int64_t N, int64_t K, void* stream);
 /* post_attention_layernorm + router (top-2 of 8) as a stand-alone kernel (the decode step uses the fused form below). */
 int vita_decode_router(const void* h, const void* norm_w, const void* gate_w, void* xn, int32_t* topk_ids,
                        float* topk_w, int64_t B, int64_t H, int64_t E, float eps, void* stream);
-/* post_attention_layernorm + router (fused, recomputed per CTA) + the two selected experts' gate/up rows:
- * act[b,k,:] = silu(gate) * up; also writes topk_ids / topk_w [B,2] for the down kernel.
- * vita_decode_moe_down: h[b] += sum_k w_k * down_k(act[b,k]). */
-int vita_decode_moe_gate_up(const void* h, const void* norm_w, const void* gate_w, const void* w13, int32_t* topk_ids,
-                            float* topk_w, void* act, int64_t B, int64_t H, int64_t I, int64_t E, float eps,
-                            void* stream);
-int vita_decode_moe_down(const void* act, const void* w2, const int32_t* topk_ids, const float* topk_w, void* h,
-                         int64_t B, int64_t H, int64_t I, void* stream);
-/* final RMSNorm + lm_head on one row per sequence + arg-max on the bf16 logits (vita_mixtral.py:171-173 and the
- * greedy step of HF generate(), video_audio_demo.py:257-270).  logits may be NULL; best[b] must be 0 on entry. */
-int vita_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
-                        uint64_t* best, int64_t B, int64_t H, int64_t V, float eps, void* stream);
-
 /* batched decode through the GEMM path: per-sequence KV slots of the current positions, row-wise arg-max of bf16
  * logits into the packed `best` words the decode chain consumes. */
 int vita_decode_slots(const int32_t* cur_pos, const int32_t* block_table, int32_t* slots, int64_t B, int64_t page_size,
                       int64_t max_pages, void* stream);
 int vita_argmax_rows(const void* logits, uint64_t* best, int64_t B, int64_t V, void* stream);
-/* hint: pull `bytes` at `ptr` into L2 (cp.async.bulk.prefetch.L2), e.g. the o-projection weights during attention */
-int vita_l2_prefetch(const void* ptr, int64_t bytes, void* stream);
-
 /* ---- greedy decode step on the tensor cores (tcgen05 swap-AB GEMV, stream-K) ---------------------------------
- * Same operations and epilogues as the vita_decode_* entry points above, with the weight tile as the M operand of
+ * Every linear of the decode step as a weight-streaming GEMV on the tensor cores: the weight tile is the M operand of
  * tcgen05.mma and the activation vector as row 0 of a 16-wide N operand; (row-block, k-block) units are split evenly
  * over all SMs and combined through `workspace` (vita_decode_tc_workspace_bytes, zero-initialised once, shared by all
  * five calls; ws_row_blocks = the max_row_blocks it was sized for): K-partials travel as 64-bit {value, tag} words,
@@ -267,25 +244,6 @@ int vita_decode_tc_moe_down(const void* act, const void* w2, const int32_t* topk
 int vita_tc_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
                            uint64_t* best, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H, int64_t V,
                            float eps, void* stream);
-
-/* ---- single-kernel decode step (bs = 1) -------------------------------------------------------------------
- * All linears of all layers, the paged attention and the LM head as phases of ONE persistent launch separated by
- * grid barriers (decode_mega.cu): the TMA producer streams the next phase's weights while the epilogue warps cross
- * the barrier.  vita_mega_build writes the device-resident tensor maps / per-layer pointer table once;
- * vita_mega_decode_step runs one token (precede it with vita_decode_embed and zero `grid_bar`). */
-int64_t vita_mega_maps_bytes(int64_t n_layers);
-int64_t vita_mega_layers_bytes(int64_t n_layers);
-int64_t vita_mega_workspace_floats(int64_t max_row_blocks);
-int vita_mega_build(void* maps_out, void* layers_out, int64_t n_layers, const void* const* wqkv, const void* const* wo,
-                    const void* const* w13, const void* const* w2, const void* const* ln1, const void* const* ln2,
-                    const void* const* gate, void* const* k_cache, void* const* v_cache, const void* lm_head, int64_t H,
-                    int64_t I, int64_t E, int64_t n_q, int64_t n_kv, int64_t V);
-int vita_mega_decode_step(const void* maps, const void* layers, int64_t n_layers, const void* final_norm, void* h,
-                          void* q, void* attn, void* act, void* logits, uint64_t* best, const float* cos_sin,
-                          const int32_t* cur_pos, const int32_t* block_table, float* scratch, int32_t* tickets,
-                          uint32_t* grid_bar, float* attn_part_o, float* attn_part_ml, int32_t* attn_tickets, int64_t H,
-                          int64_t I, int64_t n_q, int64_t n_kv, int64_t V, int64_t page_size, int64_t max_pages,
-                          int64_t splits, float eps, float attn_scale, void* stream);
 
 #ifdef __cplusplus
 }

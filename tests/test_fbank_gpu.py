@@ -67,3 +67,16 @@ def test_features_feed_the_encoder(proc):
     mat, n_tok = ap.process_waveform(torch.from_numpy(GOLD["speech_1s_wave"]), 16000)
     out = model.encode_audios(mat[None], torch.tensor([mat.shape[0]]))
     assert out["inputs_embeds"].shape[1] == n_tok
+
+
+def test_other_sample_rates_warn_or_refuse(proc):
+    """whale/init_model.py:41-56 featurises non-16 kHz audio with the ORIGINAL rate's window / mel banks; vita_fbank is
+    the 16 kHz geometry: the deviation is announced (warning) or refused (strict_reference)."""
+    from vita_b200.audio_frontend import AudioProcessor
+    wave = torch.randn(44100) * 0.1
+    with pytest.warns(UserWarning, match="original rate"):
+        mat, n_tok = proc.process_waveform(wave, 44100)
+    assert mat.shape[1] == 80 and abs(mat.shape[0] - 98) <= 1          # 1 s -> ~98 frames at 16 kHz
+    strict = AudioProcessor("cuda", strict_reference=True)
+    with pytest.raises(NotImplementedError, match="original rate"):
+        strict.process_waveform(wave, 44100)

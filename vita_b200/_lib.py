@@ -33,7 +33,6 @@ SIGNATURES = {
     "vita_decode_attention": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, I64, P]),
     "vita_decode_slots": (c_int, [P, P, P, I64, I64, I64, P]),
     "vita_argmax_rows": (c_int, [P, P, I64, I64, P]),
-    "vita_l2_prefetch": (c_int, [P, I64, P]),
     "vita_moe_router": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_float, P]),
     "vita_moe_align": (c_int, [P, P, P, P, P, P, P, I64, I64, P]),
     "vita_moe_gemm_down_ep": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, I64, P]),
@@ -58,24 +57,13 @@ SIGNATURES = {
     "vita_decode_embed": (c_int, [P, P, P, I64, P, P, P, P, I64, I64, I64, I64, P, P]),
     "vita_chain_begin": (c_int, [P, I64]),
     "vita_chain_end": (c_int, []),
-    "vita_decode_qkv_rope": (c_int, [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, P]),
-    "vita_decode_oproj": (c_int, [P, P, P, I64, I64, I64, P]),
     "vita_decode_router": (c_int, [P, P, P, P, P, P, I64, I64, I64, c_float, P]),
-    "vita_decode_moe_gate_up": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
-    "vita_decode_moe_down": (c_int, [P, P, P, P, P, I64, I64, I64, P]),
-    "vita_lm_head_argmax": (c_int, [P, I64, P, P, P, P, I64, I64, I64, c_float, P]),
     "vita_decode_tc_workspace_bytes": (I64, [I64, I64]),
     "vita_decode_tc_qkv_rope": (c_int, [P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, c_float, P]),
     "vita_decode_tc_oproj": (c_int, [P, P, P, P, I64, I64, I64, I64, P]),
     "vita_decode_tc_moe_gate_up": (c_int, [P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, c_float, P]),
     "vita_decode_tc_moe_down": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, I64, P]),
     "vita_tc_lm_head_argmax": (c_int, [P, I64, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
-    "vita_mega_maps_bytes": (I64, [I64]),
-    "vita_mega_layers_bytes": (I64, [I64]),
-    "vita_mega_workspace_floats": (I64, [I64]),
-    "vita_mega_build": (c_int, [P, P, I64, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64]),
-    "vita_mega_decode_step": (c_int, [P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64,
-                                      I64, I64, I64, c_float, c_float, P]),
 }
 
 

@@ -53,7 +53,8 @@ class AudioProcessor:
     callers that already hold samples."""
 
     def __init__(self, device="cuda", num_mel_bins: int = 80, frame_length_ms: float = 25.0, frame_shift_ms: float = 10.0,
-                 dither: float = 0.0, sample_rate: int = SAMPLE_RATE):
+                 dither: float = 0.0, sample_rate: int = SAMPLE_RATE, strict_reference: bool = False):
+        self.strict_reference = strict_reference
         if dither != 0.0:
             raise ValueError("vita_b200 computes the deterministic filterbank only (dither must be 0.0)")
         self.device = torch.device(device)
@@ -76,6 +77,19 @@ class AudioProcessor:
         if waveform.dim() == 2:
             waveform = waveform[0]
         if sample_rate != self.sample_rate:
+            # DEVIATION (documented in DESIGN.md): the reference resamples to 16 kHz (init_model.py:41-45) but then
+            # calls kaldi.fbank with sample_frequency = the ORIGINAL rate (:48-56), so its window length and mel banks
+            # follow the original rate (e.g. 1102-sample frames / 2048-point spectrum for 44.1 kHz).  vita_fbank is the
+            # 25 ms / 512-point filterbank of 16 kHz audio; the features of non-16 kHz files therefore differ from the
+            # reference's.  `strict_reference=True` refuses instead of deviating.
+            if self.strict_reference:
+                raise NotImplementedError(
+                    f"sample rate {sample_rate}: the reference derives the filterbank from the original rate "
+                    "(whale/init_model.py:48-56); vita_fbank implements the 16 kHz geometry only")
+            import warnings
+            warnings.warn(f"audio at {sample_rate} Hz is resampled to {self.sample_rate} Hz and featurised with the "
+                          "16 kHz filterbank; the reference would use window / mel banks of the original rate "
+                          "(whale/init_model.py:48-56)", stacklevel=2)
             import torchaudio  # reference behaviour: CPU resampler (init_model.py:41-45)
             waveform = torchaudio.transforms.Resample(orig_freq=sample_rate, new_freq=self.sample_rate)(waveform.cpu().float())
         wave = waveform.to(self.device, torch.float32).contiguous() * float(1 << 15)

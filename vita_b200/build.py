@@ -60,11 +60,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJDIR.mkdir(parents=True, exist_ok=True)
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile_one(s, OBJDIR), srcs))
-    cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
+    tmp = LIB.with_suffix(".so.tmp")          # link aside, then rename: a reader never sees a half-written library
+    cmd = [NVCC, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
            "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, LIB)
     stamp.write_text(digest)
     if verbose:
         for s in srcs:

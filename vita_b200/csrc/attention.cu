@@ -457,8 +457,18 @@ extern "C" int vita_decode_attention(const void* q, const void* k_cache, const v
     // the all-to-all protocol needs the split count to divide the 4 x 128 outputs into <= 128-wide slices
     // ... and every CTA of a kv head polls its peers, so all of them have to be resident at once: keep that to grids
     // that fit the machine (two 128-thread CTAs per SM), larger batches take the ticket variant
+    // (real occupancy of the tagged variant, not an estimate: every CTA of the grid polls its peers)
+    static int resident_per_sm = -1;
+    if (resident_per_sm < 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_attn_kernel<true>, 128, 0) != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = 1;
+        }
+        resident_per_sm = n > 2 ? 2 : n;   // a chain neighbour may share the SM under programmatic launch
+    }
     const bool tagged = option("attn_tagged") && (splits == 4 || splits == 8 || splits == 16) &&
-                        splits * n_kv_heads * B <= 2ll * (num_sms() > 0 ? num_sms() : 148);
+                        splits * n_kv_heads * B <= static_cast<long long>(resident_per_sm) * (num_sms() > 0 ? num_sms() : 148);
     {
         static int carveout = -1;
         const int want = option("smem_carveout_max") ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutDefault;

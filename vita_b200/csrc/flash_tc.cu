@@ -262,7 +262,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 0; i < 128; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
             const float m_new = fmaxf(m_ref, mx * p.scale_log2);
             const bool grow = m_new > m_ref + 8.0f;
             if (__any_sync(0xffffffffu, grow)) {
@@ -284,20 +284,22 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             }
             const float m_use = (m_ref == -INFINITY) ? 0.0f : m_ref;
-            float sum = 0.0f;
+            float2 sum2 = make_float2(0.0f, 0.0f);
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {   // 32 scores -> 16 packed bf16 pairs -> P columns [16c, 16c + 16)
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float a0 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * i]), p.scale_log2, -m_use));
-                    const float a1 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), p.scale_log2, -m_use));
-                    sum += a0 + a1;
-                    pk[i] = pack_bf16(a0, a1);
+                    const float2 x = ffma2(make_float2(__uint_as_float(v[c * 32 + 2 * i]), __uint_as_float(v[c * 32 + 2 * i + 1])),
+                                           sc2, nm2);
+                    const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    sum2 = fadd2(sum2, a);
+                    pk[i] = pack_bf16(a.x, a.y);
                 }
                 tmem_st_32x16(tS + c * 16, pk);
             }
-            l += sum;
+            l += sum2.x + sum2.y;
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_ready[t]);

@@ -97,20 +97,12 @@ class MixtralDecoder:
         self.d_act = torch.zeros(B, 2, I, dtype=BF16, device=dev)
         self.d_logits = torch.zeros(B, cfg.vocab_size, dtype=BF16, device=dev)
         self.attn_ws = ops.decode_attention_workspace(B, cfg.num_key_value_heads, self.decode_splits, dev)
-        # decode linears: tcgen05 swap-AB GEMV (default) or the SIMT streaming GEMV (VITA_B200_GEMV=simt)
-        self.use_tc = os.environ.get("VITA_B200_GEMV", "tc") != "simt" and H % 64 == 0 and I % 128 == 0
+        # decode linears: tcgen05 swap-AB GEMVs (decode_tc.cu); their stream-K partial sums meet in one workspace
+        if H % 64 or I % 128:
+            raise ValueError("the decode GEMVs need hidden_size % 64 == 0 and intermediate_size % 128 == 0")
         max_rb = max((cfg.vocab_size + 127) // 128, 2 * (I // 128), cfg.num_attention_heads
                      + 2 * cfg.num_key_value_heads, (H + 127) // 128)
-        self.tc_ws = ops.TcWorkspace(B, max_rb, dev) if self.use_tc else None
-        # L2 prefetch of the o-projection weights during the decode attention (VITA_B200_L2PF=1)
-        self.l2_prefetch = os.environ.get("VITA_B200_L2PF", "0") == "1"
-        self._side = torch.cuda.Stream(device=dev) if self.l2_prefetch else None
-        # single-kernel decode step (bs = 1): VITA_B200_DECODE=mega
-        self.mega = None
-        if os.environ.get("VITA_B200_DECODE", "kernels") == "mega" and self.use_tc and weights.get("ep", (0, 1))[1] == 1:
-            self.mega = ops.MegaDecode(weights["layers"], weights["lm_head"], self.cache.k, self.cache.v, H, I,
-                                       cfg.num_local_experts, cfg.num_attention_heads, cfg.num_key_value_heads,
-                                       cfg.vocab_size, self.decode_splits, dev)
+        self.tc_ws = ops.TcWorkspace(B, max_rb, dev)
         # completion counters of the bs = 1 decode chain: [serial, one counter per chain kernel (5 per layer + LM head)]
         self.chain_mem = torch.zeros(2 + 5 * cfg.num_hidden_layers, dtype=torch.int64, device=dev)
         self._graphs = {}             # single-sequence decode step: captured CUDA graph per (B, want_logits)
@@ -302,12 +294,8 @@ class MixtralDecoder:
         # first generated token: final norm + lm_head + arg-max on the last row only
         self.best[slot:slot + 1].zero_()
         last_logits = self.d_logits[slot:slot + 1] if (want_last_logits or all_logits) else None
-        if self.use_tc:
-            ops.tc_lm_head_argmax(h[S - 1:], H, w["norm"], w["lm_head"], last_logits, self.best[slot:slot + 1], 1,
-                                  self.tc_ws, c.rms_norm_eps)
-        else:
-            ops.lm_head_argmax(h[S - 1:], H, w["norm"], w["lm_head"], last_logits, self.best[slot:slot + 1], 1,
-                               c.rms_norm_eps)
+        ops.tc_lm_head_argmax(h[S - 1:], H, w["norm"], w["lm_head"], last_logits, self.best[slot:slot + 1], 1,
+                              self.tc_ws, c.rms_norm_eps)
         if all_logits:
             return ops.linear(xn, w["lm_head"])      # [S, V]; xn = final RMSNorm(h) written by the last combine
         return last_logits
@@ -383,78 +371,43 @@ class MixtralDecoder:
         last_logits = None
         if t0 <= S - 1 < t1:     # this rank owns the last token: first generated token
             last_logits = self.d_logits[slot:slot + 1] if (want_last_logits or all_logits) else None
-            if self.use_tc:
-                ops.tc_lm_head_argmax(sy["h"][S - 1:S], H, w["norm"], w["lm_head"], last_logits,
-                                      self.best[slot:slot + 1], 1, self.tc_ws, c.rms_norm_eps)
-            else:
-                ops.lm_head_argmax(sy["h"][S - 1:S], H, w["norm"], w["lm_head"], last_logits,
-                                   self.best[slot:slot + 1], 1, c.rms_norm_eps)
+            ops.tc_lm_head_argmax(sy["h"][S - 1:S], H, w["norm"], w["lm_head"], last_logits,
+                                  self.best[slot:slot + 1], 1, self.tc_ws, c.rms_norm_eps)
         if all_logits:
             return ops.linear(xn_own, w["lm_head"]) if n else torch.empty(0, c.vocab_size, dtype=BF16, device=self.device)
         return last_logits
 
     # ------------------------------------------------------------------------------------------ decode
     def _decode_step_kernels(self, B: int, want_logits: bool):
+        """One greedy token for slots [0, B): embed + per layer (qkv+RoPE+KV append -> paged attention -> o-proj ->
+        router+gate/up -> down) + LM head with arg-max, 2 + 5 L launches chained by programmatic dependent launch.
+        For B = 1 the kernels are additionally linked by completion counters (include/vita_b200.h, vita_chain_begin)."""
         c, w, cache = self.cfg, self.w, self.cache
         nq, nkv, D = c.num_attention_heads, c.num_key_value_heads, c.head_dim
         h = self.d_h[:B]
-        chained = B == 1 and self.use_tc and self.mega is None and not self.l2_prefetch
+        ws = self.tc_ws
+        chained = B == 1
         ops.decode_embed(self.best[:B], self.token_log[:B], self.gen_count[:B], cache.cache_len[:B], cache.cur_pos[:B],
                          w["embed"], h, cache.max_seq_len, self.chain_mem if chained else None)
         if chained:
             ops.chain_begin(self.chain_mem)
         try:
-            self._decode_layers(B, want_logits, h)
-        finally:
-            if chained:
-                ops.chain_end()
-
-    def _decode_layers(self, B: int, want_logits: bool, h):
-        c, w, cache = self.cfg, self.w, self.cache
-        nq, nkv, D = c.num_attention_heads, c.num_key_value_heads, c.head_dim
-        if self.mega is not None and B == 1:
-            self.mega.step(w["norm"], h, self.d_q[:1], self.d_attn[:1], self.d_act[:1],
-                           self.d_logits[:1] if want_logits else None, self.best[:1], w["rope"], cache.cur_pos[:1],
-                           cache.block_table[:1], cache.page_size, c.rms_norm_eps, D ** -0.5)
-            self._log_scores(B, want_logits)
-            return
-        tc, ws = self.use_tc, self.tc_ws
-        l2pf = self.l2_prefetch
-        main = torch.cuda.current_stream()
-        for li, lw in enumerate(w["layers"]):
-            if tc:
+            for li, lw in enumerate(w["layers"]):
                 ops.decode_tc_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
                                        self.d_q[:B], cache.k[li], cache.v[li], ws, nq, nkv, D, cache.page_size,
                                        c.rms_norm_eps)
-            else:
-                ops.decode_qkv_rope(h, lw["ln1"], lw["wqkv"], w["rope"], cache.cur_pos[:B], cache.block_table[:B],
-                                    self.d_q[:B], cache.k[li], cache.v[li], nq, nkv, D, cache.page_size, c.rms_norm_eps)
-            if l2pf:
-                ev = torch.cuda.Event()
-                ev.record(main)                       # after the qkv kernel: HBM is idle during attention
-                self._side.wait_event(ev)
-                with torch.cuda.stream(self._side):
-                    ops.l2_prefetch(lw["wo"])
-            ops.decode_attention(self.d_q[:B], cache.k[li], cache.v[li], cache.block_table[:B], cache.cur_pos[:B],
-                                 self.d_attn[:B], self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits,
-                                 D ** -0.5)
-            if tc:
+                ops.decode_attention(self.d_q[:B], cache.k[li], cache.v[li], cache.block_table[:B], cache.cur_pos[:B],
+                                     self.d_attn[:B], self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits,
+                                     D ** -0.5)
                 ops.decode_tc_oproj(self.d_attn[:B], lw["wo"], h, ws)
                 ops.decode_tc_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B],
                                           self.d_act[:B], ws, c.rms_norm_eps)
                 ops.decode_tc_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h, ws)
-            else:
-                ops.decode_oproj(self.d_attn[:B], lw["wo"], h)
-                ops.decode_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B],
-                                       self.d_act[:B], c.rms_norm_eps)
-                ops.decode_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h)
-        if l2pf:
-            main.wait_stream(self._side)             # join (required to end a graph capture)
-        lg = self.d_logits[:B] if want_logits else None
-        if tc:
+            lg = self.d_logits[:B] if want_logits else None
             ops.tc_lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, ws, c.rms_norm_eps)
-        else:
-            ops.lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, c.rms_norm_eps)
+        finally:
+            if chained:
+                ops.chain_end()
         self._log_scores(B, want_logits)
 
     def enable_score_log(self):
@@ -474,7 +427,7 @@ class MixtralDecoder:
 
     @property
     def launches_per_decode_step(self) -> int:
-        return 2 if self.mega is not None else 2 + 5 * self.cfg.num_hidden_layers
+        return 2 + 5 * self.cfg.num_hidden_layers
 
     def launches_per_decode_step_with_scores(self) -> int:
         return self.launches_per_decode_step + 1

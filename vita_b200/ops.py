@@ -141,10 +141,6 @@ def decode_slots(cur_pos, block_table, slots, page_size):
               block_table.shape[1], _stream())
 
 
-def l2_prefetch(t: torch.Tensor):
-    _lib.call("vita_l2_prefetch", _p(t), t.numel() * t.element_size(), _stream())
-
-
 def argmax_rows(logits, best):
     _chk(logits, BF16, "logits"); _chk(best, torch.int64, "best")
     _lib.call("vita_argmax_rows", _p(logits), _p(best), logits.shape[0], logits.shape[1], _stream())
@@ -317,41 +313,10 @@ def chain_end():
     _lib.call("vita_chain_end")
 
 
-def decode_qkv_rope(h, norm_w, w_qkv, cos_sin, cur_pos, block_table, q_out, k_cache, v_cache, n_q, n_kv, head_dim,
-                    page_size, eps):
-    B, H = h.shape
-    _lib.call("vita_decode_qkv_rope", _p(h), _p(norm_w), _p(w_qkv), _p(cos_sin), _p(cur_pos), _p(block_table),
-              _p(q_out), _p(k_cache), _p(v_cache), B, H, n_q, n_kv, head_dim, page_size, block_table.shape[1],
-              float(eps), _stream())
-
-
-def decode_oproj(x, w, h):
-    B, N = h.shape
-    _lib.call("vita_decode_oproj", _p(x), _p(w), _p(h), B, N, w.shape[1], _stream())
-
-
 def decode_router(h, norm_w, gate_w, xn, topk_ids, topk_w, eps):
     B, H = h.shape
     _lib.call("vita_decode_router", _p(h), _p(norm_w), _p(gate_w), _p(xn), _p(topk_ids), _p(topk_w), B, H,
               gate_w.shape[0], float(eps), _stream())
-
-
-def decode_moe_gate_up(h, norm_w, gate_w, w13, topk_ids, topk_w, act, eps):
-    """Fused post-attention RMSNorm + router + selected experts' gate/up GEMV; writes topk_ids / topk_w."""
-    B, H = h.shape
-    _lib.call("vita_decode_moe_gate_up", _p(h), _p(norm_w), _p(gate_w), _p(w13), _p(topk_ids), _p(topk_w), _p(act), B, H,
-              w13.shape[1] // 2, gate_w.shape[0], float(eps), _stream())
-
-
-def decode_moe_down(act, w2, topk_ids, topk_w, h):
-    B, H = h.shape
-    _lib.call("vita_decode_moe_down", _p(act), _p(w2), _p(topk_ids), _p(topk_w), _p(h), B, H, w2.shape[2], _stream())
-
-
-def lm_head_argmax(h, h_stride, norm_w, w, logits, best, B, eps):
-    V, H = w.shape
-    _lib.call("vita_lm_head_argmax", _p(h), h_stride, _p(norm_w), _p(w), _p(logits), _p(best), B, H, V, float(eps),
-              _stream())
 
 
 # ------------------------------------------------------------------------------------------------ decode step (tcgen05)
@@ -396,37 +361,6 @@ def tc_lm_head_argmax(h, h_stride, norm_w, w, logits, best, B, ws, eps):
 
 
 # ------------------------------------------------------------------------------------------------ single-kernel decode
-class MegaDecode:
-    """Device-resident tensor maps / layer table + workspaces of the single-kernel decode step (bs = 1)."""
-
-    def __init__(self, layers, lm_head, k_caches, v_caches, H, I, E, n_q, n_kv, V, splits, device):
-        lib = _lib.load()
-        L = len(layers)
-        self.L, self.H, self.I, self.n_q, self.n_kv, self.V, self.splits = L, H, I, n_q, n_kv, V, splits
-        self.maps = torch.zeros(lib.vita_mega_maps_bytes(L) + 64, dtype=torch.uint8, device=device)
-        self.layers = torch.zeros(lib.vita_mega_layers_bytes(L), dtype=torch.uint8, device=device)
-        arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
-        _lib.call("vita_mega_build", _p(self.maps), _p(self.layers), L, arr([l["wqkv"] for l in layers]),
-                  arr([l["wo"] for l in layers]), arr([l["w13"] for l in layers]), arr([l["w2"] for l in layers]),
-                  arr([l["ln1"] for l in layers]), arr([l["ln2"] for l in layers]), arr([l["gate"] for l in layers]),
-                  arr(k_caches), arr(v_caches), _p(lm_head), H, I, E, n_q, n_kv, V)
-        max_rb = max((V + 127) // 128, 2 * (I // 128), n_q + 2 * n_kv, (H + 127) // 128)
-        self.scratch = torch.zeros(lib.vita_mega_workspace_floats(max_rb), dtype=torch.float32, device=device)
-        self.tickets = torch.zeros(max_rb, dtype=torch.int32, device=device)
-        self.grid_bar = torch.zeros(1, dtype=torch.int32, device=device)
-        self.attn_part_o = torch.zeros(n_kv * splits * 4 * 128, dtype=torch.float32, device=device)
-        self.attn_part_ml = torch.zeros(n_kv * splits * 4 * 2, dtype=torch.float32, device=device)
-        self.attn_tickets = torch.zeros(n_kv, dtype=torch.int32, device=device)
-
-    def step(self, final_norm, h, q, attn, act, logits, best, cos_sin, cur_pos, block_table, page_size, eps, scale):
-        self.grid_bar.zero_()
-        _lib.call("vita_mega_decode_step", _p(self.maps), _p(self.layers), self.L, _p(final_norm), _p(h), _p(q),
-                  _p(attn), _p(act), _p(logits), _p(best), _p(cos_sin), _p(cur_pos), _p(block_table), _p(self.scratch),
-                  _p(self.tickets), _p(self.grid_bar), _p(self.attn_part_o), _p(self.attn_part_ml),
-                  _p(self.attn_tickets), self.H, self.I, self.n_q, self.n_kv, self.V, page_size, block_table.shape[1],
-                  self.splits, float(eps), float(scale), _stream())
-
-
 def launch_count(reset: bool = False) -> int:
     return int(_lib.load().vita_launch_count(1 if reset else 0))
 
