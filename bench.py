@@ -484,15 +484,6 @@ def run_b200(args):
         llm.reset()
     barrier()
 
-    # ---- N > 1: the expert-parallel configs[3] record (collective over all ranks) ------------------------------
-    ep_rec = None
-    if world > 1 and not args.no_ep:
-        try:
-            ep_rec = run_ep_record(args, cfg, model, dev, rank, world)
-        except Exception as e:
-            ep_rec = {"error": f"{type(e).__name__}: {e}"[:400]}
-        barrier()
-
     # ---- long prefill (S = 4096): where the expert GEMMs are compute-bound -----------------------------------
     long_ms = None
     if not args.no_long_prefill:
@@ -585,7 +576,7 @@ def run_b200(args):
                             "as video_audio_demo.py:257-270; CUDA-graph decode with the device-side logits log",
                     "gpu_launches": int(e2e_launches)},
             "parity": parity,
-            "ep": ep_rec,
+            "ep": None,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }
@@ -599,9 +590,40 @@ def run_b200(args):
                           f"{cfg.llm.num_hidden_layers}), S={s['S']}, {args.cpu_decode_tokens} decode steps, best of 3 "
                           f"per phase: enc {s['t_enc']:.2f}s prefill {s['t_prefill_full']:.2f}s decode "
                           f"{s['t_dec_full'] * 1e3:.1f} ms/token"}
-        print(json.dumps(line))
+    else:
+        line = None
+
+    # ---- N > 1: the expert-parallel configs[3] record, LAST (collective over all ranks).  Everything above is already
+    # in `line`; a watchdog prints it without the record if the exchange protocol ever hangs, a Python / CUDA error
+    # lands in ep.error -- the replica measurement is never lost to this step.
+    if world > 1 and not args.no_ep:
+        done = threading.Event()
+
+        def bail():
+            if not done.is_set():
+                if line is not None:
+                    line["ep"] = {"error": "expert-parallel record did not finish within 240 s"}
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+
+        timer = threading.Timer(240.0, bail)
+        timer.daemon = True
+        timer.start()
+        try:
+            ep_rec = run_ep_record(args, cfg, model, dev, rank, world)
+        except Exception as e:
+            ep_rec = {"error": f"{type(e).__name__}: {e}"[:400]}
+        done.set()
+        timer.cancel()
+        if line is not None:
+            line["ep"] = ep_rec
+    if line is not None:
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def ncu_traffic_bytes(kernel_name: str):

@@ -33,6 +33,7 @@ struct FaParams {
     int n_qblk;                   // number of 128-row query blocks
     int pair_heads;               // NQ == 2: 1 = tiles are heads (2y, 2y+1) at the same rows, 0 = rows (2x, 2x+1)
     uint32_t v_lbo, v_sbo;        // MN-major descriptor strides of the V tile (bytes)
+    int poly_chunks;              // of the 4 column chunks of a tile, how many take exp2 on the FMA pipe (MUFU relief)
 };
 
 constexpr int FA_BM = 128;   // query rows per tile (UMMA M, TMEM lanes)
@@ -49,7 +50,7 @@ struct FaCfg {
     static constexpr int SMEM = NQ * Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int DQK, int DV, int NQ>
+template <int DQK, int DV, int NQ, int POLY>
 __global__ void __launch_bounds__(FaCfg<DQK, DV, NQ>::THREADS, 1)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FaParams p) {
@@ -293,7 +294,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int i = 0; i < 16; ++i) {
                     const float2 x = ffma2(make_float2(__uint_as_float(v[c * 32 + 2 * i]), __uint_as_float(v[c * 32 + 2 * i + 1])),
                                            sc2, nm2);
-                    const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    const float2 a = (c < POLY) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
                     sum2 = fadd2(sum2, a);
                     pk[i] = pack_bf16(a.x, a.y);
                 }
@@ -337,12 +338,12 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 }
 
-template <int DQK, int DV, int NQ>
-static int launch_flash_tc(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
-                           dim3 grid, cudaStream_t st) {
+template <int DQK, int DV, int NQ, int POLY>
+static int launch_flash_tc_p(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
+                             dim3 grid, cudaStream_t st) {
     using Cfg = FaCfg<DQK, DV, NQ>;
     static bool configured = false;
-    auto kern = flash_tc_kernel<DQK, DV, NQ>;
+    auto kern = flash_tc_kernel<DQK, DV, NQ, POLY>;
     if (!configured) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM),
                             "cudaFuncSetAttribute(flash_tc smem)");
@@ -351,6 +352,14 @@ static int launch_flash_tc(const CUtensorMap& tmQ, const CUtensorMap& tmK, const
     }
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmQ, tmK, tmV, p);
     return check_launch("flash_tc_kernel");
+}
+
+// POLY = column chunks (of 4 per key tile) whose exp2 runs as a polynomial on the FMA pipe (option "fa_poly")
+template <int DQK, int DV, int NQ>
+static int launch_flash_tc(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
+                           dim3 grid, cudaStream_t st) {
+    if (p.poly_chunks >= 1) return launch_flash_tc_p<DQK, DV, NQ, 1>(tmQ, tmK, tmV, p, grid, st);
+    return launch_flash_tc_p<DQK, DV, NQ, 0>(tmQ, tmK, tmV, p, grid, st);
 }
 
 // 4-D view (D, tokens, heads, batch) of a strided activation; box = 64 columns x 128 tokens, 128B swizzle
@@ -380,6 +389,7 @@ static int flash_tc_dispatch(const void* q, const void* k, const void* v, const 
     p.n_qblk = (p.Sq + FA_BM - 1) / FA_BM;
     p.v_lbo = option("fa_v_lbo") ? static_cast<uint32_t>(option("fa_v_lbo")) : FA_BN * 128;
     p.v_sbo = option("fa_v_sbo") ? static_cast<uint32_t>(option("fa_v_sbo")) : 1024;
+    p.poly_chunks = option("fa_poly");
     // two query tiles per CTA (softmax of one tile overlaps the tensor-core work of the other) once that still
     // fills the machine; GQA pairs two heads of a kv group at the same rows (identical causal extent and K/V tiles)
     const bool pair_heads = (p.group % 2 == 0);
