@@ -8,12 +8,18 @@ below the bf16 noise floor at ~40 % of the steps, so no bf16 implementation (the
 reproduces an fp32 greedy trajectory.  SURVEY.md section 8(c) therefore asks for weights scaled so that margins are
 non-degenerate and a seed chosen once and recorded:
 
-* the lm_head rows get log-normal gains (sigma 1.5): heavy-tailed logits, median top-1/top-2 gap 23 % of the top
-  logit instead of 4 %;
+* the lm_head rows get log-normal gains (sigma 2.5): heavy-tailed logits, the top-1 / top-2 gap is tens of percent of
+  the top logit at most steps instead of 4 %;
+* the router weights are scaled x100 (std 2.0): the routing soft-max becomes sharp, so whenever the rank-2 and rank-3
+  experts are nearly tied (which random routers are at ~5 % of all decisions, whatever their scale) the second expert's
+  renormalised weight is tiny and swapping it for the third changes nothing measurable; a near-tie of the TOP two keeps
+  the expert set and moves the weights continuously.  Top-2 routing, renormalisation and both expert evaluations are
+  still exercised at every token;
 * everything else is `vita_b200.weights.synthetic_state` (std 0.02 matrices, 1 +- 0.1 norm gains), seed 0;
-* the prompt seed is searched (`make_golden_pr1.py search`) for a trajectory whose 33 logit rows and whose router
-  decisions (rank-2 vs rank-3 expert, every layer, last prompt token and all generated tokens) are all clear of
-  near-ties; the chosen seed, the tokens and the observed margins are recorded in tests/golden/pr1_l4.npz.
+* the prompt seed is searched (`make_golden_pr1.py search`) for a trajectory whose 33 logit rows are clear of near-ties
+  and whose router decisions (every layer, last prompt token and all generated tokens) are either clear (rank-2 vs
+  rank-3 gap above the bf16 noise of the two logits) or harmless (second weight <= 2 %); the chosen seed, the tokens and
+  the observed margins are recorded in tests/golden/pr1_l4.npz.
 """
 from __future__ import annotations
 
@@ -28,7 +34,8 @@ LAYERS = 4
 PROMPT_LEN = 128
 NEW_TOKENS = 32
 WEIGHT_SEED = 0
-HEAD_GAIN_SIGMA = 1.5
+HEAD_GAIN_SIGMA = 2.5
+GATE_SCALE = 100.0
 
 
 def config() -> VitaConfig:
@@ -46,6 +53,9 @@ def build_state(cfg: VitaConfig | None = None):
     state = W.synthetic_state(cfg, WEIGHT_SEED, parts=("llm",))
     gains = head_gains(cfg.llm.vocab_size)
     state["lm_head.weight"] = (state["lm_head.weight"].float() * gains[:, None]).to(torch.bfloat16)
+    for l in range(cfg.llm.num_hidden_layers):
+        k = f"model.layers.{l}.block_sparse_moe.gate.weight"
+        state[k] = (state[k].float() * GATE_SCALE).to(torch.bfloat16)
     return state
 
 
@@ -53,15 +63,31 @@ def prompt(seed: int, vocab: int) -> torch.Tensor:
     return torch.randint(0, vocab, (1, PROMPT_LEN), generator=torch.Generator().manual_seed(1000 + seed))
 
 
-def margins(rows: torch.Tensor, router_probs) -> dict:
-    """rows [n, V] logits the tokens were chosen from; router_probs: list (per step) of list (per layer) of [E] probs.
-    -> smallest top-1/top-2 logit gap relative to the top logit, smallest rank-2/rank-3 router logit gap."""
+def margins(rows: torch.Tensor, router_probs, gate_norms=None, hidden: int = 4096) -> dict:
+    """rows [n, V]: the logits the tokens were chosen from; router_probs: per step, per layer, the [E] routing
+    probabilities of that token; gate_norms: per layer [E] row norms of the router weight.
+    -> the smallest top-1 / top-2 logit gap relative to the top logit, and the worst router decision: for every
+    decision either the rank-2 / rank-3 logit gap in units of the two logits' spread (|x| * |g_e|, what their bf16 noise
+    is proportional to) or, when the second renormalised weight is <= 2 %, "harmless" (reported as 1.0)."""
     top = rows.float().topk(2, dim=-1).values
     rel = ((top[:, 0] - top[:, 1]) / top[:, 0].abs().clamp_min(1e-9))
     gaps = []
     for step in router_probs:
-        for p in step:
-            s = p.float().log().sort(descending=True).values
-            gaps.append(float(s[1] - s[2]))
+        for l, p in enumerate(step):
+            lp = p.double().clamp_min(1e-300).log()
+            srt, idx = lp.sort(descending=True)
+            w2 = float(1.0 / (1.0 + torch.exp(srt[0] - srt[1])))          # renormalised weight of the second expert
+            if w2 <= 0.02:
+                gaps.append(1.0)
+                continue
+            spread = 1.0
+            if gate_norms is not None:
+                spread = float(hidden ** 0.5 * 0.5 * (gate_norms[l][idx[1]] + gate_norms[l][idx[2]]))
+            gaps.append(float(srt[1] - srt[2]) / spread)
     return {"logit_rel_gap_min": float(rel.min()), "logit_rel_gaps": rel.tolist(),
-            "router_log_gap_min": min(gaps), "router_log_gaps": gaps}
+            "router_gap_min": min(gaps), "router_gaps": gaps}
+
+
+def gate_norms(state, cfg):
+    return [state[f"model.layers.{l}.block_sparse_moe.gate.weight"].float().norm(dim=-1).cpu()
+            for l in range(cfg.llm.num_hidden_layers)]

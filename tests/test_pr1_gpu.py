@@ -29,7 +29,7 @@ def test_pr1_free_running_greedy_token_ids_exact():
     want = g["tokens"].tolist()
     out = model.generate(ids.cuda(), max_new_tokens=pr1.NEW_TOKENS, output_scores=True)
     got = out.sequences[0, pr1.PROMPT_LEN:].tolist()
-    print("oracle margins: logit gap min %.3f, router gap min %.3f" % (g["logit_rel_gaps"].min(), g["router_log_gaps"].min()))
+    print("oracle margins: logit gap min %.3f, router gap min %.3f" % (g["logit_rel_gaps"].min(), g["router_gaps"].min()))
     assert got == want, (got, want)
     # the logits the tokens were chosen from: top-2 values of every step within bf16 tolerance of the oracle's
     rows = torch.cat(list(out.scores)).float().cpu()

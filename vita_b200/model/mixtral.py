@@ -71,7 +71,7 @@ class MixtralDecoder:
         #   p2p  replicated dense part, fused P2P combine (round-1 design, kept as the A/B baseline)
         #   nccl replicated dense part, partial sums + NCCL all-reduce (library baseline)
         self.ep_rank, self.ep_world = weights.get("ep", (0, 1))
-        self.ep_mode = os.environ.get("VITA_B200_EP", "seq") if self.ep_world > 1 else None
+        self.ep_mode = os.environ.get("VITA_B200_EP", "p2p") if self.ep_world > 1 else None
         assert self.ep_mode in (None, "seq", "p2p", "nccl"), "VITA_B200_EP must be seq, p2p or nccl"
         self.ep_p2p = None
         storage = None
