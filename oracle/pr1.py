@@ -67,8 +67,8 @@ def margins(rows: torch.Tensor, router_probs, gate_norms=None, hidden: int = 409
     """rows [n, V]: the logits the tokens were chosen from; router_probs: per step, per layer, the [E] routing
     probabilities of that token; gate_norms: per layer [E] row norms of the router weight.
     -> the smallest top-1 / top-2 logit gap relative to the top logit, and the worst router decision: for every
-    decision either the rank-2 / rank-3 logit gap in units of the two logits' spread (|x| * |g_e|, what their bf16 noise
-    is proportional to) or, when the second renormalised weight is <= 2 %, "harmless" (reported as 1.0)."""
+    decision either the rank-2 / rank-3 logit gap in units of the two logits' spread (|g_e| * rms(x): the standard
+    deviation of such a logit, which its bf16 noise -- ~0.2-0.5 % of it -- is proportional to) or, when the second renormalised weight is <= 2 %, "harmless" (reported as 1.0)."""
     top = rows.float().topk(2, dim=-1).values
     rel = ((top[:, 0] - top[:, 1]) / top[:, 0].abs().clamp_min(1e-9))
     gaps = []
@@ -82,7 +82,7 @@ def margins(rows: torch.Tensor, router_probs, gate_norms=None, hidden: int = 409
                 continue
             spread = 1.0
             if gate_norms is not None:
-                spread = float(hidden ** 0.5 * 0.5 * (gate_norms[l][idx[1]] + gate_norms[l][idx[2]]))
+                spread = float(0.5 * (gate_norms[l][idx[1]] + gate_norms[l][idx[2]]))   # |g_e| * rms(x), rms(x) ~ 1 after RMSNorm
             gaps.append(float(srt[1] - srt[2]) / spread)
     return {"logit_rel_gap_min": float(rel.min()), "logit_rel_gaps": rel.tolist(),
             "router_gap_min": min(gaps), "router_gaps": gaps}
