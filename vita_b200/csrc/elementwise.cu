@@ -196,56 +196,75 @@ rope_kv_write_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ po
 // ------------------------------------------------------------------------------------------------ MoE router
 // post_attention_layernorm + MixtralTopKRouter (modeling_mixtral.py:109-116): logits = xn . Wg^T on the bf16-rounded
 // normed activations, fp32 softmax over E, top-2 (first index wins ties, as torch.topk), renormalise by the pair sum.
-// One warp per token.  Also writes xn (the expert GEMM input).
+// One 128-thread CTA per token (the row stays in registers between the two passes), whatever the token count: the
+// bits of a token's routing do not depend on how many tokens share the launch.  Also writes xn (the expert GEMM input).
 template <int E>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 rmsnorm_router_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ norm_w,
                       const __nv_bfloat16* __restrict__ gate_w, __nv_bfloat16* __restrict__ xn,
                       int* __restrict__ topk_ids, float* __restrict__ topk_w, int n_tok, int H, float eps) {
+    constexpr int MAXV = 4;                      // 128 threads x 4 x 8 elements = H <= 4096
+    __shared__ float red[4][E + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tok = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (tok >= n_tok) return;
+    const int tok = blockIdx.x;
     const uint4* hr = reinterpret_cast<const uint4*>(h + static_cast<long long>(tok) * H);
     const int nvec = H >> 3;
+    uint4 hv[MAXV];
     float ss = 0.0f;
-#pragma unroll 4
-    for (int i = lane; i < nvec; i += 32) {
-        float f[8];
-        unpack8(hr[i], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = threadIdx.x + j * 128;
+        if (i < nvec) {
+            hv[j] = hr[i];
+            float f[8];
+            unpack8(hv[j], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ss += f[q] * f[q];
+        }
     }
     ss = warp_sum(ss);
-    const float inv = rsqrtf(ss / static_cast<float>(H) + eps);
+    if (lane == 0) red[warp][E] = ss;
+    __syncthreads();
+    const float inv = rsqrtf((red[0][E] + red[1][E] + red[2][E] + red[3][E]) / static_cast<float>(H) + eps);
     float logit[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) logit[e] = 0.0f;
     uint4* xr = reinterpret_cast<uint4*>(xn + static_cast<long long>(tok) * H);
     const uint4* nw = reinterpret_cast<const uint4*>(norm_w);
-#pragma unroll 2
-    for (int i = lane; i < nvec; i += 32) {
-        float f[8], g[8];
-        unpack8(hr[i], f);
-        unpack8(__ldg(nw + i), g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = f[j] * inv * g[j];
-        const uint4 packed = pack8(f);
-        xr[i] = packed;
-        unpack8(packed, f);  // router sees the bf16-rounded activations
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = threadIdx.x + j * 128;
+        if (i < nvec) {
+            float f[8], g[8];
+            unpack8(hv[j], f);
+            unpack8(__ldg(nw + i), g);
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            float wv[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * H) + i), wv);
+            for (int q = 0; q < 8; ++q) f[q] = f[q] * inv * g[q];
+            const uint4 packed = pack8(f);
+            xr[i] = packed;
+            unpack8(packed, f);  // router sees the bf16-rounded activations
 #pragma unroll
-            for (int j = 0; j < 8; ++j) logit[e] += f[j] * wv[j];
+            for (int e = 0; e < E; ++e) {
+                float wv[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * H) + i), wv);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) logit[e] += f[q] * wv[q];
+            }
         }
     }
 #pragma unroll
-    for (int e = 0; e < E; ++e) logit[e] = warp_sum(logit[e]);
-    if (lane == 0) {
+    for (int e = 0; e < E; ++e) {
+        logit[e] = warp_sum(logit[e]);
+        if (lane == 0) red[warp][e] = logit[e];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         float m = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < E; ++e) m = fmaxf(m, logit[e]);
+        for (int e = 0; e < E; ++e) {
+            logit[e] = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+            m = fmaxf(m, logit[e]);
+        }
         float p[E], sum = 0.0f;
 #pragma unroll
         for (int e = 0; e < E; ++e) { p[e] = expf(logit[e] - m); sum += p[e]; }
@@ -751,9 +770,9 @@ extern "C" int vita_rope_kv_write(void* qkv, const int32_t* positions, const int
 extern "C" int vita_moe_router(const void* h, const void* norm_w, const void* gate_w, void* xn, int32_t* topk_ids,
                                float* topk_w, int64_t n_tok, int64_t H, int64_t E, float eps, void* stream) {
     VITA_REQUIRE(E == 8, "router is specialised for 8 experts (Mixtral-8x7B)");
-    VITA_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    VITA_REQUIRE(H % 8 == 0 && H <= 4096, "H must be a multiple of 8 and <= 4096");
     if (n_tok == 0) return VITA_OK;
-    const unsigned grid = static_cast<unsigned>((n_tok + 3) / 4);
+    const unsigned grid = static_cast<unsigned>(n_tok);
     rmsnorm_router_kernel<8><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         BF(h), BF(norm_w), BF(gate_w), BFM(xn), topk_ids, topk_w, (int)n_tok, (int)H, eps);
     return check_launch("moe_router");
