@@ -43,8 +43,9 @@ def config() -> VitaConfig:
 
 
 def head_gains(vocab: int) -> torch.Tensor:
-    g = torch.Generator().manual_seed(zlib.crc32(b"pr1.lm_head.row_gain"))
-    return torch.exp(HEAD_GAIN_SIGMA * torch.randn(vocab, generator=g))
+    with torch.device("cpu"):
+        g = torch.Generator(device="cpu").manual_seed(zlib.crc32(b"pr1.lm_head.row_gain"))
+        return torch.exp(HEAD_GAIN_SIGMA * torch.randn(vocab, generator=g))
 
 
 def build_state(cfg: VitaConfig | None = None):
@@ -60,7 +61,8 @@ def build_state(cfg: VitaConfig | None = None):
 
 
 def prompt(seed: int, vocab: int) -> torch.Tensor:
-    return torch.randint(0, vocab, (1, PROMPT_LEN), generator=torch.Generator().manual_seed(1000 + seed))
+    with torch.device("cpu"):      # the search runs under a cuda default device; the prompt is host data
+        return torch.randint(0, vocab, (1, PROMPT_LEN), generator=torch.Generator(device="cpu").manual_seed(1000 + seed))
 
 
 def margins(rows: torch.Tensor, router_probs, gate_norms=None, hidden: int = 4096) -> dict:

@@ -61,10 +61,31 @@ class StreamedOracle:
 
 
 @torch.no_grad()
-def check_mixtral(model, emb: torch.Tensor, n_tokens: int = 8) -> dict:
+def check_mixtral(model, emb: torch.Tensor, n_tokens: int = 8, sharpen_router: float = 128.0) -> dict:
     """`model`: vita_b200 VITAMixtralForCausalLM; `emb` [S, H] bf16 spliced prompt embeddings (consumed by value).
     Runs prefill + n_tokens greedy steps on both sides; the oracle is teacher-forced with ITS OWN tokens, the CUDA path
-    runs free; reports the first-row logit error, the token agreement and the oracle's margins."""
+    runs free; reports the first-row logit error, the token agreement and the oracle's margins.
+
+    `sharpen_router`: random-init routers put ~4 % of all (token, layer) decisions within bf16 noise of a rank-2 / rank-3
+    tie; a flipped expert replaces that layer's whole MoE output, and over 32 layers x S tokens the bf16 and fp32
+    trajectories decorrelate completely (observed: relative logit error 1.1 with every kernel correct).  For the duration
+    of the check the router weights of BOTH sides are multiplied by this power of two (exact in bf16, exactly undone
+    afterwards): the routing soft-max becomes sharp, the second expert of a near-tied pair carries a negligible weight,
+    and the comparison measures the arithmetic instead of the chaos.  1.0 = leave the weights alone."""
+    llm = model.llm
+    cfg = model.config.llm
+    if sharpen_router != 1.0:
+        for lw in model.packed["llm"]["layers"]:
+            lw["gate"].mul_(sharpen_router)
+    try:
+        return _check_mixtral(model, emb, n_tokens, sharpen_router)
+    finally:
+        if sharpen_router != 1.0:
+            for lw in model.packed["llm"]["layers"]:
+                lw["gate"].div_(sharpen_router)
+
+
+def _check_mixtral(model, emb, n_tokens, sharpen_router):
     llm = model.llm
     cfg = model.config.llm
     orc = StreamedOracle(model.packed["llm"], cfg, emb.device)
@@ -93,7 +114,7 @@ def check_mixtral(model, emb: torch.Tensor, n_tokens: int = 8) -> dict:
     # rows are comparable while both sides have consumed the same tokens: row i depends on tokens < i
     cmp = min(n_same + 1, n_tokens)
     err = (got_rows[:cmp] - ref_rows[:cmp]).abs().amax(-1) / ref_rows[:cmp].abs().amax(-1)
-    return {"tokens": n_tokens, "ids_equal_prefix": n_same, "oracle_ids": ref_toks, "cuda_ids": got_toks,
+    return {"tokens": n_tokens, "router_weights_scaled_by": sharpen_router, "ids_equal_prefix": n_same, "oracle_ids": ref_toks, "cuda_ids": got_toks,
             "first_row_rel_err": float(err[0]), "max_row_rel_err_on_common_prefix": float(err.max()),
             "oracle_top2_rel_gap": rel_gap,
             "first_mismatch_gap": None if n_same == n_tokens else rel_gap[n_same]}

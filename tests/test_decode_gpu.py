@@ -56,4 +56,5 @@ def test_decode_embed_bookkeeping():
     assert cur.cpu().tolist() == [11, 21, 30] and clen.cpu().tolist() == [12, 22, 31]
     cnt.copy_(torch.tensor([1, 2, 4], dtype=torch.int32)); clen.copy_(torch.tensor([11, 21, 31], dtype=torch.int32))
     assert cnt.cpu().tolist() == [1, 2, 4] and best.cpu().tolist() == [0, 0, 0]
-    assert log.cpu().tolist() == [[7, -1, -1, -1], [-1, 99, -1, -1], [-1, -1, -1, 0]]
+    # both calls logged their token (the second one token 1 at counts 1, 2; count 4 is past the 4-entry log)
+    assert log.cpu().tolist() == [[7, 1, -1, -1], [-1, 99, 1, -1], [-1, -1, -1, 0]]

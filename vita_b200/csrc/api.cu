@@ -66,10 +66,10 @@ static Option g_options[] = {
     {"tc_prefetch_consts", "VITA_B200_TC_PREFETCH_CONSTS", 1, {-1}},
     // FlashAttention (flash_tc.cu): force the number of query tiles per CTA (0 = heuristic, 1, 2)
     // decode chain: per-kernel completion counters polled by the successor instead of griddepcontrol.wait
-    {"chain_counters", "VITA_B200_CHAIN_COUNTERS", 0, {-1}},
-    {"fa_nq", "VITA_B200_FA_NQ", 1, {-1}},
+    {"chain_counters", "VITA_B200_CHAIN_COUNTERS", 1, {-1}},
+    {"fa_nq", "VITA_B200_FA_NQ", 0, {-1}},
     // FlashAttention: column chunks (of 4 per key tile) whose exp2 runs as a polynomial on the FMA pipe
-    {"fa_poly", "VITA_B200_FA_POLY", 0, {-1}},
+    {"fa_poly", "VITA_B200_FA_POLY", 1, {-1}},
     // bring-up aids: override the MN-major V descriptor strides in bytes (0 = derived from the tile shape)
     {"fa_v_lbo", "VITA_B200_FA_V_LBO", 0, {-1}},
     {"fa_v_sbo", "VITA_B200_FA_V_SBO", 0, {-1}},

@@ -173,7 +173,7 @@ class VITAMixtralForCausalLM:
         self.audio_encoder = AudioEncoder(cfg.audio, cfg.llm.hidden_size, packed["audio"], device) \
             if "audio" in packed else None
         import os
-        self._captured = CapturedEncoders(self) if os.environ.get("VITA_B200_ENC_GRAPH", "0") == "1" else None
+        self._captured = CapturedEncoders(self) if os.environ.get("VITA_B200_ENC_GRAPH", "1") == "1" else None
 
     # -- surface helpers ------------------------------------------------------------------------------------
     def eval(self):
