@@ -52,19 +52,21 @@ def oracle_greedy(state, cfg, ids, n_new):
 
 
 def cmd_search(args):
+    """For every router scale in --scales (powers of two: exact in bf16) walk the prompt seeds, compute the oracle's
+    trajectory and margins, and run the CUDA path on every seed whose logit margins qualify."""
     on_gpu = torch.cuda.is_available()      # a GPU makes a candidate cost ~0.2 s instead of ~35 s; the CPU works too
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     cfg = pr1.config()
     t0 = time.time()
-    state_bf16 = pr1.build_state(cfg)
+    state_bf16 = pr1.build_state(cfg, gate_scale=1.0)
     print(f"[pr1] state built in {time.time() - t0:.0f}s", flush=True)
     dev = "cuda" if on_gpu else "cpu"
     if on_gpu:
         torch.set_default_device("cuda")
         state = {k: v.to("cuda").float() for k, v in state_bf16.items()}
     else:
-        state = state_bf16
+        state = {k: v.clone() for k, v in state_bf16.items()}
     model = None
     try:
         if not on_gpu:
@@ -75,31 +77,49 @@ def cmd_search(args):
                                        max_new_tokens=pr1.NEW_TOKENS)
     except Exception as e:   # pragma: no cover
         print("[pr1] CUDA path unavailable:", e, flush=True)
-    out = {"criteria": {"logit_rel_gap_min": LOGIT_GAP_MIN, "router_gap_min": ROUTER_GAP_MIN}, "candidates": []}
-    gnorms = pr1.gate_norms(state_bf16, cfg)
-    n_ok = 0
-    for seed in range(args.first, args.max):
-        ids = pr1.prompt(seed, cfg.llm.vocab_size).to(dev)
-        toks, rows, probs = oracle_greedy(state, cfg, ids, pr1.NEW_TOKENS)
-        m = pr1.margins(rows.cpu(), [[p.cpu() for p in s] for s in probs], gnorms, cfg.llm.hidden_size)
-        ok = m["logit_rel_gap_min"] >= LOGIT_GAP_MIN and m["router_gap_min"] >= ROUTER_GAP_MIN
-        rec = {"prompt_seed": seed, "logit_rel_gap_min": m["logit_rel_gap_min"],
-               "router_gap_min": m["router_gap_min"], "ok": ok, "tokens": toks, "distinct_tokens": len(set(toks))}
-        if model is not None and (ok or seed < 8):
-            with torch.device("cpu"):
-                got = model.generate(ids.cpu(), max_new_tokens=pr1.NEW_TOKENS).sequences[0, pr1.PROMPT_LEN:].tolist()
-            rec["cuda_tokens_equal"] = got == toks
-            rec["cuda_first_diff"] = next((i for i, (a, b) in enumerate(zip(got, toks)) if a != b), None)
-        if ok or seed < 8 or not on_gpu:
-            out["candidates"].append(rec)
-            print("[pr1]", json.dumps({k: v for k, v in rec.items() if k != "tokens"}), flush=True)
-        n_ok += ok
-        if n_ok >= args.want:
-            break
-    out["seeds_tried"] = seed + 1
+    gkeys = [f"model.layers.{l}.block_sparse_moe.gate.weight" for l in range(cfg.llm.num_hidden_layers)]
+    out = {"criteria": {"logit_rel_gap_min": LOGIT_GAP_MIN, "router_gap_min": ROUTER_GAP_MIN}, "scales": {}}
+    cur = 1.0
+    for scale in [float(x) for x in args.scales.split(",")]:
+        f = scale / cur
+        for l, k in enumerate(gkeys):                      # rescale the routers of both sides in place
+            state[k] = state[k] * f
+            state_bf16[k] = (state_bf16[k].float() * f).to(torch.bfloat16)
+            if model is not None:
+                model.packed["llm"]["layers"][l]["gate"].mul_(f)
+        cur = scale
+        gnorms = pr1.gate_norms(state_bf16, cfg)
+        cands, n_ok, n_run, n_eq = [], 0, 0, 0
+        for seed in range(args.first, args.max):
+            ids = pr1.prompt(seed, cfg.llm.vocab_size).to(dev)
+            toks, rows, probs = oracle_greedy(state, cfg, ids, pr1.NEW_TOKENS)
+            m = pr1.margins(rows.cpu(), [[p.cpu() for p in s] for s in probs], gnorms, cfg.llm.hidden_size)
+            logit_ok = m["logit_rel_gap_min"] >= LOGIT_GAP_MIN
+            ok = logit_ok and m["router_gap_min"] >= ROUTER_GAP_MIN
+            rec = {"prompt_seed": seed, "logit_rel_gap_min": m["logit_rel_gap_min"],
+                   "router_gap_min": m["router_gap_min"], "weight_noise_max": m["weight_noise_max"], "ok": ok,
+                   "tokens": toks, "distinct_tokens": len(set(toks))}
+            if model is not None and logit_ok:
+                with torch.device("cpu"):
+                    got = model.generate(ids.cpu(), max_new_tokens=pr1.NEW_TOKENS).sequences[0, pr1.PROMPT_LEN:].tolist()
+                rec["cuda_tokens_equal"] = got == toks
+                rec["cuda_first_diff"] = next((i for i, (a, b) in enumerate(zip(got, toks)) if a != b), None)
+                if rec["cuda_first_diff"] is not None:
+                    rec["gap_at_first_diff"] = m["logit_rel_gaps"][rec["cuda_first_diff"]]
+                n_run += 1
+                n_eq += rec["cuda_tokens_equal"]
+            if logit_ok or not on_gpu:
+                cands.append(rec)
+                print(f"[pr1] scale {scale:g}", json.dumps({k: v for k, v in rec.items() if k != "tokens"}), flush=True)
+            n_ok += ok
+            if n_ok >= args.want:
+                break
+        out["scales"][f"{scale:g}"] = {"candidates": cands, "seeds_tried": seed + 1 - args.first,
+                                       "cuda_runs": n_run, "cuda_equal": n_eq}
+        print(f"[pr1] scale {scale:g}: {n_ok} margin-qualified seed(s) in {seed + 1 - args.first}; CUDA path equal on "
+              f"{n_eq} of {n_run} logit-qualified seeds, {time.time() - t0:.0f}s", flush=True)
     Path("gpurun_out").mkdir(exist_ok=True)
     Path(f"gpurun_out/pr1_search{'' if on_gpu else '_cpu'}.json").write_text(json.dumps(out, indent=1))
-    print(f"[pr1] {n_ok} candidate(s) in {seed + 1} seeds, {time.time() - t0:.0f}s")
 
 
 def reference_greedy(state_bf16, cfg, ids, n_new):
@@ -179,7 +199,7 @@ def main():
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
     s = sub.add_parser("search"); s.add_argument("--max", type=int, default=400); s.add_argument("--want", type=int, default=3)
-    s.add_argument("--first", type=int, default=0)
+    s.add_argument("--first", type=int, default=0); s.add_argument("--scales", default=str(pr1.GATE_SCALE))
     m = sub.add_parser("mint"); m.add_argument("--prompt-seed", type=int, required=True)
     m.add_argument("--reference", action="store_true")
     args = ap.parse_args()

@@ -48,15 +48,16 @@ def head_gains(vocab: int) -> torch.Tensor:
         return torch.exp(HEAD_GAIN_SIGMA * torch.randn(vocab, generator=g))
 
 
-def build_state(cfg: VitaConfig | None = None):
+def build_state(cfg: VitaConfig | None = None, gate_scale: float | None = None):
     """Reference-named bf16 state dict of the PR1 model (LLM part only)."""
     cfg = cfg or config()
+    gate_scale = GATE_SCALE if gate_scale is None else gate_scale
     state = W.synthetic_state(cfg, WEIGHT_SEED, parts=("llm",))
     gains = head_gains(cfg.llm.vocab_size)
     state["lm_head.weight"] = (state["lm_head.weight"].float() * gains[:, None]).to(torch.bfloat16)
     for l in range(cfg.llm.num_hidden_layers):
         k = f"model.layers.{l}.block_sparse_moe.gate.weight"
-        state[k] = (state[k].float() * GATE_SCALE).to(torch.bfloat16)
+        state[k] = (state[k].float() * gate_scale).to(torch.bfloat16)
     return state
 
 
@@ -73,12 +74,17 @@ def margins(rows: torch.Tensor, router_probs, gate_norms=None, hidden: int = 409
     deviation of such a logit, which its bf16 noise -- ~0.2-0.5 % of it -- is proportional to) or, when the second renormalised weight is <= 2 %, "harmless" (reported as 1.0)."""
     top = rows.float().topk(2, dim=-1).values
     rel = ((top[:, 0] - top[:, 1]) / top[:, 0].abs().clamp_min(1e-9))
-    gaps = []
+    gaps, wnoise = [], 0.0
     for step in router_probs:
         for l, p in enumerate(step):
             lp = p.double().clamp_min(1e-300).log()
             srt, idx = lp.sort(descending=True)
             w2 = float(1.0 / (1.0 + torch.exp(srt[0] - srt[1])))          # renormalised weight of the second expert
+            if gate_norms is not None:
+                # expected bf16 noise of the mixing weights: d w2 = w2 (1 - w2) d(logit_1 - logit_2), with the noise of
+                # a router logit ~0.4 % of its spread |g_e| * rms(x)
+                sp12 = float(0.5 * (gate_norms[l][idx[0]] + gate_norms[l][idx[1]]))
+                wnoise = max(wnoise, 0.006 * sp12 * w2 * (1.0 - w2))
             if w2 <= 0.02:
                 gaps.append(1.0)
                 continue
@@ -87,7 +93,7 @@ def margins(rows: torch.Tensor, router_probs, gate_norms=None, hidden: int = 409
                 spread = float(0.5 * (gate_norms[l][idx[1]] + gate_norms[l][idx[2]]))   # |g_e| * rms(x), rms(x) ~ 1 after RMSNorm
             gaps.append(float(srt[1] - srt[2]) / spread)
     return {"logit_rel_gap_min": float(rel.min()), "logit_rel_gaps": rel.tolist(),
-            "router_gap_min": min(gaps), "router_gaps": gaps}
+            "router_gap_min": min(gaps), "router_gaps": gaps, "weight_noise_max": wnoise}
 
 
 def gate_norms(state, cfg):

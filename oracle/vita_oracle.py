@@ -249,12 +249,22 @@ def expert_weights(state, lcfg, l, e):
     return state[p + "w1.weight"], state[p + "w3.weight"], state[p + "w2.weight"]
 
 
-def sparse_moe(state, lcfg, l, xn, trace=None):
-    """MixtralSparseMoeBlock / MixtralExperts.forward, modeling_mixtral.py:74-98,127-136; xn [T, H]."""
-    probs, top_v, top_i = router_topk(xn, state[f"model.layers.{l}.block_sparse_moe.gate.weight"],
-                                      lcfg.num_experts_per_tok)
+def sparse_moe(state, lcfg, l, xn, trace=None, route=None):
+    """MixtralSparseMoeBlock / MixtralExperts.forward, modeling_mixtral.py:74-98,127-136; xn [T, H].
+
+    `route` (checker aid, default None = the reference's own routing): {"ids": [T, 2] expert ids}.  The two experts of
+    every token are then the given ones, their weights the oracle's OWN soft-max probabilities of those two experts,
+    renormalised (:113-115 applied to the given pair); the dict receives "logits" [T, E] (the oracle's router logits)
+    and "own_ids" [T, 2] (the pair the oracle itself would have picked) so the caller can judge every difference."""
+    gate_w = state[f"model.layers.{l}.block_sparse_moe.gate.weight"]
+    probs, top_v, top_i = router_topk(xn, gate_w, lcfg.num_experts_per_tok)
     if trace is not None:
         trace["router_probs"] = probs
+    if route is not None:
+        route["logits"], route["own_ids"] = linear(xn, gate_w).float(), top_i
+        top_i = route["ids"].to(top_i.device).long()
+        top_v = probs.gather(1, top_i)
+        top_v = top_v / top_v.sum(dim=-1, keepdim=True)
     out = torch.zeros_like(xn)
     for e in range(lcfg.num_local_experts):
         tok, kpos = torch.where(top_i == e)
@@ -268,7 +278,7 @@ def sparse_moe(state, lcfg, l, xn, trace=None):
     return out, top_i, top_v
 
 
-def decoder_layer(state, lcfg, l, h, positions, past_kv=None, trace=None):
+def decoder_layer(state, lcfg, l, h, positions, past_kv=None, trace=None, route=None):
     """MixtralDecoderLayer.forward :365-390 + MixtralAttention.forward :312-351 (eager/sdpa causal GQA).
 
     h [B, S, H]; positions [B, S]; past_kv = (k, v) each [B, n_kv, P, D] or None.  Returns (h, (k, v))."""
@@ -297,7 +307,7 @@ def decoder_layer(state, lcfg, l, h, positions, past_kv=None, trace=None):
     xn = rmsnorm(h, state[p + "post_attention_layernorm.weight"], lcfg.rms_norm_eps)
     if trace is not None:
         trace["h_mid"] = h
-    y, _, _ = sparse_moe(state, lcfg, l, xn.reshape(-1, H), trace)
+    y, _, _ = sparse_moe(state, lcfg, l, xn.reshape(-1, H), trace, route)
     return h + y.reshape(B, S, H), (k, v)                                                           # :386-389
 
 

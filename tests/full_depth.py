@@ -38,8 +38,12 @@ class StreamedOracle:
         torch.backends.cudnn.allow_tf32 = False
 
     @torch.no_grad()
-    def forward(self, emb: torch.Tensor) -> torch.Tensor:
-        """emb [1, S, H] (any float dtype) -> last-row logits [V] fp32; appends to the KV cache."""
+    def forward(self, emb: torch.Tensor, routes=None, stats=None, keep_cache: bool = True) -> torch.Tensor:
+        """emb [1, S, H] (any float dtype) -> last-row logits [V] fp32; appends to the KV cache.
+
+        `routes`: per layer (ids [S, 2], weights [S, 2]) of the CUDA path for the same tokens: the oracle then evaluates
+        the experts the CUDA path chose (with its own fp32 weights for that pair) and `stats` collects, per decision,
+        how the given pair relates to the oracle's own."""
         with torch.device(self.dev):
             c = self.c
             past_len = 0 if self.past is None else self.past[0][0].shape[2]
@@ -49,10 +53,22 @@ class StreamedOracle:
             new_past = []
             for l in range(c.num_hidden_layers):
                 st = layer_state(self.w, c, l)
-                h, kv = O.decoder_layer(st, c, l, h, pos, None if self.past is None else self.past[l])
+                route = None if routes is None else {"ids": routes[l][0]}
+                h, kv = O.decoder_layer(st, c, l, h, pos, None if self.past is None else self.past[l], None, route)
+                if route is not None and stats is not None:
+                    lg, own, ids = route["logits"], route["own_ids"], route["ids"].long()
+                    gap = lg.gather(1, own).sum(-1) - lg.gather(1, ids).sum(-1)            # >= 0, 0 iff the same pair
+                    differs = (own.sort(-1).values != ids.sort(-1).values).any(-1)
+                    pr = torch.softmax(lg, -1).gather(1, ids)
+                    w_orc = pr / pr.sum(-1, keepdim=True)
+                    stats["decisions"] += int(ids.shape[0])
+                    stats["differ"] += int(differs.sum())
+                    stats["gaps"].append((gap / lg.std(-1).clamp_min(1e-9))[differs].cpu())
+                    stats["weight_errs"].append((w_orc - routes[l][1].float()).abs().amax(-1).cpu())
                 new_past.append(kv)
                 del st
-            self.past = new_past
+            if keep_cache:
+                self.past = new_past
             hn = O.rmsnorm(h[:, -1:], self.w["norm"].float(), c.rms_norm_eps)
             return O.linear(hn, self.w["lm_head"].float())[0, -1]
 
@@ -61,60 +77,72 @@ class StreamedOracle:
 
 
 @torch.no_grad()
-def check_mixtral(model, emb: torch.Tensor, n_tokens: int = 8, sharpen_router: float = 128.0) -> dict:
+def check_mixtral(model, emb: torch.Tensor, n_tokens: int = 8) -> dict:
     """`model`: vita_b200 VITAMixtralForCausalLM; `emb` [S, H] bf16 spliced prompt embeddings (consumed by value).
-    Runs prefill + n_tokens greedy steps on both sides; the oracle is teacher-forced with ITS OWN tokens, the CUDA path
-    runs free; reports the first-row logit error, the token agreement and the oracle's margins.
 
-    `sharpen_router`: random-init routers put ~4 % of all (token, layer) decisions within bf16 noise of a rank-2 / rank-3
-    tie; a flipped expert replaces that layer's whole MoE output, and over 32 layers x S tokens the bf16 and fp32
-    trajectories decorrelate completely (observed: relative logit error 1.1 with every kernel correct).  For the duration
-    of the check the router weights of BOTH sides are multiplied by this power of two (exact in bf16, exactly undone
-    afterwards): the routing soft-max becomes sharp, the second expert of a near-tied pair carries a negligible weight,
-    and the comparison measures the arithmetic instead of the chaos.  1.0 = leave the weights alone."""
+    The CUDA path runs prefill + free-running greedy decode (eager launches, logits of every step logged, the top-2
+    expert pair of every (token, layer) recorded through MixtralDecoder.route_trace).  The fp32 oracle then replays the
+    SAME token sequence with the SAME expert pairs ("routing-aligned": the experts are the CUDA path's, their mixing
+    weights and everything else the oracle's own fp32 arithmetic), so every logits row is comparable and the comparison
+    measures the arithmetic.  Why aligned: random-init routers put a few percent of all (token, layer) decisions within
+    bf16 noise of a rank-2 / rank-3 tie; a flipped expert replaces half of that token's MoE output and, over 32 layers x
+    S tokens, the bf16 and fp32 trajectories decorrelate whatever the kernels do (measured: last-row relative error
+    ~1.1 unaligned with unit routers, 0.49 with the routers sharpened x128 -- reported below as `unaligned_...`).  Every
+    decision where the CUDA pair differs from the oracle's own is judged instead: the oracle's logit gap between the two
+    pairs, in units of the token's router-logit spread, must be at noise level (`routing_max_gap_over_spread`), and the
+    CUDA path's mixing weights must match the oracle's for the same pair (`routing_max_weight_err`)."""
     llm = model.llm
     cfg = model.config.llm
-    if sharpen_router != 1.0:
-        for lw in model.packed["llm"]["layers"]:
-            lw["gate"].mul_(sharpen_router)
-    try:
-        return _check_mixtral(model, emb, n_tokens, sharpen_router)
-    finally:
-        if sharpen_router != 1.0:
-            for lw in model.packed["llm"]["layers"]:
-                lw["gate"].div_(sharpen_router)
-
-
-def _check_mixtral(model, emb, n_tokens, sharpen_router):
-    llm = model.llm
-    cfg = model.config.llm
-    orc = StreamedOracle(model.packed["llm"], cfg, emb.device)
-    row = orc.forward(emb[None])
-    ref_rows, ref_toks = [row], [int(row.argmax())]
-    for _ in range(n_tokens - 1):
-        row = orc.forward(orc.embed(ref_toks[-1]))
-        ref_rows.append(row)
-        ref_toks.append(int(row.argmax()))
-    ref_rows = torch.stack(ref_rows)
-    # CUDA path: free-running greedy with the logits of every step
+    L = cfg.num_hidden_layers
+    # ---- CUDA path, free running
     llm.check_capacity(emb.shape[0], n_tokens)
     llm.reset()
     log = llm.enable_score_log()
-    first = llm.prefill(emb.clone().contiguous(), slot=0, want_last_logits=True)
-    log[0].copy_(first[0])
-    for _ in range(n_tokens):
-        llm.decode_step(1, use_graph=False, want_logits=True)
+    llm.route_trace = []
+    try:
+        first = llm.prefill(emb.clone().contiguous(), slot=0, want_last_logits=True)
+        log[0].copy_(first[0])
+        for _ in range(n_tokens):
+            llm.decode_step(1, use_graph=False, want_logits=True)
+        trace = llm.route_trace
+    finally:
+        llm.route_trace = None
+    assert len(trace) == L * (1 + n_tokens)
     got_toks = llm.generated_tokens(0)[:n_tokens]
     got_rows = log[:n_tokens].float()
+    # ---- oracle, same tokens, same expert pairs
+    orc = StreamedOracle(model.packed["llm"], cfg, emb.device)
+    stats = {"decisions": 0, "differ": 0, "gaps": [], "weight_errs": []}
+    unaligned_row = orc.forward(emb[None], keep_cache=False)                  # information: the oracle's own routing
+    rows = [orc.forward(emb[None], trace[:L], stats)]
+    for k in range(n_tokens - 1):
+        rows.append(orc.forward(orc.embed(got_toks[k]), trace[(1 + k) * L:(2 + k) * L], stats))
+    ref_rows = torch.stack(rows)
+    ref_toks = ref_rows.argmax(-1).tolist()
     top = ref_rows.topk(2, dim=-1).values
     rel_gap = ((top[:, 0] - top[:, 1]) / top[:, 0].abs().clamp_min(1e-9)).tolist()
-    n_same = 0
-    while n_same < n_tokens and got_toks[n_same] == ref_toks[n_same]:
-        n_same += 1
-    # rows are comparable while both sides have consumed the same tokens: row i depends on tokens < i
-    cmp = min(n_same + 1, n_tokens)
-    err = (got_rows[:cmp] - ref_rows[:cmp]).abs().amax(-1) / ref_rows[:cmp].abs().amax(-1)
-    return {"tokens": n_tokens, "router_weights_scaled_by": sharpen_router, "ids_equal_prefix": n_same, "oracle_ids": ref_toks, "cuda_ids": got_toks,
-            "first_row_rel_err": float(err[0]), "max_row_rel_err_on_common_prefix": float(err.max()),
-            "oracle_top2_rel_gap": rel_gap,
-            "first_mismatch_gap": None if n_same == n_tokens else rel_gap[n_same]}
+    err = ((got_rows - ref_rows).abs().amax(-1) / ref_rows.abs().amax(-1)).tolist()
+    # a token id is decided when the oracle's top-1 / top-2 gap exceeds twice the measured error of that row
+    decided = [rel_gap[i] > 2 * err[i] for i in range(n_tokens)]
+    un_err = float((got_rows[0] - unaligned_row).abs().max() / unaligned_row.abs().max())
+    gaps = torch.cat(stats["gaps"]) if stats["gaps"] else torch.zeros(1)
+    gaps = gaps if gaps.numel() else torch.zeros(1)
+    werr = torch.cat(stats["weight_errs"])
+    q = lambda t, f: float(t.float().quantile(f)) if t.numel() > 1 else float(t.max())
+    return {"tokens": n_tokens, "mode": "routing-aligned (oracle evaluates the CUDA path's expert pairs on the CUDA path's tokens)",
+            "cuda_ids": got_toks, "oracle_ids": ref_toks, "row_rel_err": err, "max_row_rel_err": max(err),
+            "first_row_rel_err": err[0], "oracle_top2_rel_gap": rel_gap,
+            "ids_decided": int(sum(decided)), "ids_equal_where_decided": int(sum(1 for i in range(n_tokens)
+                                                                                 if decided[i] and got_toks[i] == ref_toks[i])),
+            "ids_equal": int(sum(1 for a, b in zip(got_toks, ref_toks) if a == b)),
+            "routing_decisions": stats["decisions"], "routing_differ": stats["differ"],
+            "routing_differ_frac": stats["differ"] / max(1, stats["decisions"]),
+            # of the decisions that differ: the oracle's logit gap between its own pair and the CUDA pair, in units of
+            # the token's router-logit spread (std over the 8 experts); bf16 drift of the hidden state is a few percent
+            "routing_differ_gap_over_spread_median": q(gaps, 0.5), "routing_differ_gap_over_spread_p99": q(gaps, 0.99),
+            "routing_differ_gap_over_spread_max": float(gaps.max()),
+            # all decisions: |CUDA mixing weight - oracle mixing weight of the same pair|
+            "routing_weight_err_median": q(werr, 0.5), "routing_weight_err_p99": q(werr, 0.99),
+            "routing_weight_err_max": float(werr.max()),
+            "unaligned_first_row_rel_err": un_err,
+            "unaligned_first_id_equal": bool(int(unaligned_row.argmax()) == got_toks[0])}

@@ -41,13 +41,16 @@ def test_configs2_full_depth_prefill_and_greedy_vs_streamed_fp32_oracle():
     assert lens == [506]
     assert_close(emb, ref_emb, rel=4e-2, what="full-size spliced inputs_embeds (InternViT 24L + Whale 24L + adapter)")
     del st
-    # (2) 32 layers: prefill last-row logits + 8 free-running greedy tokens
+    # (2) 32 layers: prefill last-row logits + 8 free-running greedy tokens, against the routing-aligned fp32 oracle
     r = check_mixtral(model, emb[0], n_tokens=8)
     print(r)
-    assert r["first_row_rel_err"] < 6e-2
-    assert r["max_row_rel_err_on_common_prefix"] < 8e-2
-    # ids: equal up to the first step where the oracle itself has a near-tie (random-init weights: flat distributions)
-    clear = 0
-    while clear < 8 and r["oracle_top2_rel_gap"][clear] > 0.08:
-        clear += 1
-    assert r["ids_equal_prefix"] >= clear, r
+    # measured (profiles/r02_full_depth_parity.json): rows 0.03-0.06 after 32 bf16 layers, unaligned 0.45
+    assert r["max_row_rel_err"] < 8e-2, r                        # every logits row (prefill + 7 decode steps)
+    assert r["ids_equal_where_decided"] == r["ids_decided"], r   # every id the oracle decides beyond the row's error
+    assert r["ids_equal"] >= 6, r                                # and most of the others (flat random-init logits)
+    # routing: the CUDA path's expert pair differs from the oracle's own only at ties within the drift of the hidden
+    # state (a few percent of the router-logit spread; extreme value over ~16k decisions below 0.5), and its mixing
+    # weights are the oracle's
+    assert r["routing_differ_frac"] < 0.06, r
+    assert r["routing_differ_gap_over_spread_p99"] < 0.25 and r["routing_differ_gap_over_spread_max"] < 0.6, r
+    assert r["routing_weight_err_p99"] < 0.04 and r["routing_weight_err_max"] < 0.12, r

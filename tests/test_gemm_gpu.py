@@ -53,6 +53,26 @@ def test_gemm_model_shapes():
     _run(256, 4096, 4096, bias=True, act=1)      # projector
 
 
+def test_gemm_tail_split_shapes():
+    # tiles of the last partial wave are cut along N (gemm_sm100.cu Sched): 148-SM tile counts with a short tail
+    _run(2048, 5120, 512, bias=True)             # 256-wide: 320 tiles = 2 waves + 24 -> pieces of 64 columns
+    _run(2048, 3328, 512, residual=True)         # 208 tiles = 1 wave + 60 -> pieces of 128 columns
+    _run(1025, 3072, 256, bias=True, act=1)      # 128-wide: 216 tiles = 1 wave + 68 -> pieces of 64 columns
+    _run(4096, 4096, 1024, residual=True)        # o_proj at S=4096: 512 tiles = 3 waves + 68
+
+
+def test_gemm_tail_split_is_bit_identical_to_whole_tiles(monkeypatch):
+    import os
+    from vita_b200 import ops
+    x, w = to_dev(randn((2048, 1024), 5, 1.0)), to_dev(randn((5120, 1024), 6, 0.05))
+    monkeypatch.setenv("VITA_B200_GEMM_TAIL_SPLIT", "0")
+    whole = ops.linear(x, w).clone()
+    monkeypatch.setenv("VITA_B200_GEMM_TAIL_SPLIT", "1")
+    cut = ops.linear(x, w)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, cut)
+
+
 def test_gemm_many_tiles_persistent():
     # more tiles than SMs -> every CTA loops (smem ring phase wrap, both TMEM accumulator stages)
     _run(1536, 8192, 512, bias=True)

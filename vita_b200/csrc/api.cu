@@ -64,9 +64,10 @@ static Option g_options[] = {
     {"tc_trigger_lead", "VITA_B200_TC_TRIGGER_LEAD", 0, {-1}},
     // tcgen05 decode kernels: pull norm / router weights into L2 ahead of the dependency wait
     {"tc_prefetch_consts", "VITA_B200_TC_PREFETCH_CONSTS", 1, {-1}},
-    // FlashAttention (flash_tc.cu): force the number of query tiles per CTA (0 = heuristic, 1, 2)
     // decode chain: per-kernel completion counters polled by the successor instead of griddepcontrol.wait
-    {"chain_counters", "VITA_B200_CHAIN_COUNTERS", 1, {-1}},
+    // (same-box A/B, profiles/r02_decode_ab.txt: 5.24 ms/token with the counters, 5.12 without -> off)
+    {"chain_counters", "VITA_B200_CHAIN_COUNTERS", 0, {-1}},
+    // FlashAttention (flash_tc.cu): force the number of query tiles per CTA (0 = heuristic, 1, 2)
     {"fa_nq", "VITA_B200_FA_NQ", 0, {-1}},
     // FlashAttention: column chunks (of 4 per key tile) whose exp2 runs as a polynomial on the FMA pipe
     {"fa_poly", "VITA_B200_FA_POLY", 1, {-1}},

@@ -40,15 +40,58 @@ struct GemmArgs {
     const int* row_assign;
     __nv_bfloat16* const* peer_out;
     int chunk;
+    int tail_split;             // cut the tiles of the last partial wave along N (see Sched)
 };
 
 struct Tile {
     int group, m0, m_end, n0;
+    int bn;   // MMA N of this work item: BLOCK_N for a whole tile, BLOCK_N / split for a piece of a tail tile
 };
 
-// Tile order inside a group: n-block major, m-block minor, so CTAs that run together share the weight tile in L2.
-template <int BN_OUT>
-__device__ __forceinline__ bool tile_at(const GemmArgs& a, int tile_idx, Tile& t) {
+// Work list of one launch.  Tiles are ordered group-major, n-block major, m-block minor (CTAs that run together share
+// the weight tile in L2) and dealt round-robin to the persistent CTAs.  The tiles of the last, partly filled wave are
+// cut along N into `split` pieces (2 or 4) when that still fits one wave: a 512-tile problem on 148 SMs then costs
+// 3 + 1/2 waves instead of 4, a 1040-tile one 7 + 1/4 instead of 8.  (The fused gate|up variant is not cut: its N
+// tile is two half tiles and it runs ~50 waves.)
+struct Sched {
+    int total;      // whole tiles
+    int full_end;   // tiles [0, full_end) are processed whole
+    int split;      // the others in `split` pieces each
+    __device__ __forceinline__ int items() const { return full_end + (total - full_end) * split; }
+};
+
+template <int BLOCK_N, int BN_OUT, bool SILU>
+__device__ __forceinline__ Sched make_sched(const GemmArgs& a) {
+    const int num_n = (a.N + BN_OUT - 1) / BN_OUT;
+    int total = 0;
+    for (int g = 0; g < a.num_groups; ++g) {
+        const int r0 = a.group_offsets ? a.group_offsets[g] : 0;
+        const int r1 = a.group_offsets ? a.group_offsets[g + 1] : a.M;
+        total += ((r1 - r0 + 127) >> 7) * num_n;
+    }
+    Sched s{total, total, 1};
+    if (!SILU && a.tail_split) {
+        const int G = static_cast<int>(gridDim.x);
+        const int R = total % G;
+        constexpr int MAX_SPLIT = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // pieces of at least 32 columns, at most 4
+        int sp = 1;
+        while (R > 0 && sp * 2 <= MAX_SPLIT && sp * 2 * R <= G) sp *= 2;
+        if (sp > 1) { s.full_end = total - R; s.split = sp; }
+    }
+    return s;
+}
+
+template <int BLOCK_N, int BN_OUT>
+__device__ __forceinline__ bool tile_at(const GemmArgs& a, const Sched& sc, int item, Tile& t) {
+    if (item >= sc.items()) return false;
+    int tile_idx = item, part = 0;
+    t.bn = BLOCK_N;
+    if (item >= sc.full_end) {
+        const int j = item - sc.full_end;
+        tile_idx = sc.full_end + j / sc.split;
+        part = j % sc.split;
+        t.bn = BLOCK_N / sc.split;
+    }
     const int num_n = (a.N + BN_OUT - 1) / BN_OUT;
     int base = 0;
     for (int g = 0; g < a.num_groups; ++g) {
@@ -59,7 +102,7 @@ __device__ __forceinline__ bool tile_at(const GemmArgs& a, int tile_idx, Tile& t
         if (tile_idx < base + nt) {
             const int local = tile_idx - base;
             t.group = g;
-            t.n0 = (local / mt) * BN_OUT;
+            t.n0 = (local / mt) * BN_OUT + part * t.bn;
             t.m0 = r0 + (local % mt) * 128;
             t.m_end = r1;
             return true;
@@ -72,6 +115,7 @@ __device__ __forceinline__ bool tile_at(const GemmArgs& a, int tile_idx, Tile& t
 template <int BLOCK_N, bool SILU, int STAGES>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmBs /* B in boxes of 32 rows: pieces of tail tiles */,
                     const GemmArgs args) {
     constexpr int BLOCK_M = 128, BLOCK_K = 64;
     constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -97,6 +141,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (!SILU) tma_prefetch_desc(&tmBs);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -122,12 +167,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             Tile t;
-            for (int tile = blockIdx.x; tile_at<BN_OUT>(args, tile, t); tile += gridDim.x) {
+            const Sched sc = make_sched<BLOCK_N, BN_OUT, SILU>(args);
+            for (int tile = blockIdx.x; tile_at<BLOCK_N, BN_OUT>(args, sc, tile, t); tile += gridDim.x) {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + t.bn * (BLOCK_K * 2));
                     tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, t.m0);
-                    if constexpr (SILU) {
+                    if (!SILU && t.bn != BLOCK_N) {
+                        for (int r = 0; r < t.bn; r += 32)
+                            tma_load_3d(sB + stage * B_BYTES + r * (BLOCK_K * 2), &tmBs, &full_bar[stage], kb * BLOCK_K,
+                                        t.n0 + r, t.group);
+                    } else if constexpr (SILU) {
                         // gate rows [n0, n0+128) and up rows [N + n0, N + n0 + 128) of the fused [2N, K] weight
                         tma_load_3d(sB + stage * B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, t.n0, t.group);
                         tma_load_3d(sB + stage * B_BYTES + B_BYTES / 2, &tmB, &full_bar[stage], kb * BLOCK_K,
@@ -142,14 +192,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) {
             // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
             Tile t;
-            for (int tile = blockIdx.x; tile_at<BN_OUT>(args, tile, t); tile += gridDim.x) {
+            const Sched sc = make_sched<BLOCK_N, BN_OUT, SILU>(args);
+            for (int tile = blockIdx.x; tile_at<BLOCK_N, BN_OUT>(args, sc, tile, t); tile += gridDim.x) {
+                const uint32_t idesc = umma_idesc_bf16(BLOCK_M, t.bn);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -177,7 +228,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         Tile t;
-        for (int tile = blockIdx.x; tile_at<BN_OUT>(args, tile, t); tile += gridDim.x) {
+        const Sched sc = make_sched<BLOCK_N, BN_OUT, SILU>(args);
+        for (int tile = blockIdx.x; tile_at<BLOCK_N, BN_OUT>(args, sc, tile, t); tile += gridDim.x) {
+            const int n_chunks = (SILU ? BN_OUT : t.bn) / 32;
             mbar_wait(&tmem_full[acc], acc_phase, 4);
             tc_fence_after();
             const int grow = t.m0 + quad * 32 + lane;
@@ -193,7 +246,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             const __nv_bfloat16* rrow = args.residual ? args.residual + static_cast<long long>(grow) * args.ldr : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < BN_OUT / 32; ++c) {
+            for (int c = 0; c < n_chunks; ++c) {
                 const int col0 = t.n0 + c * 32;
                 if (col0 >= args.N) break;  // warp-uniform
                 uint32_t v[32];
@@ -310,8 +363,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int BLOCK_N, bool SILU, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int max_tiles,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBs, const GemmArgs& args,
+                       int max_tiles, cudaStream_t stream) {
     constexpr int smem_bytes = STAGES * (128 * 64 * 2 + BLOCK_N * 64 * 2) + 1024 + 256;
     static bool configured = false;
     auto kern = gemm_bf16_tn_kernel<BLOCK_N, SILU, STAGES>;
@@ -322,9 +375,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
         configured = true;
     }
     int grid = num_sms();
-    if (max_tiles < grid) grid = max_tiles;
+    // with the tail split a problem of fewer tiles than SMs still spreads over the whole machine
+    const long long items = static_cast<long long>(max_tiles) * ((!SILU && args.tail_split) ? (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4) : 1);
+    if (items < grid) grid = static_cast<int>(items);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, args);
+    kern<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, tmBs, args);
     return check_launch("gemm_bf16_tn_kernel");
 }
 
@@ -348,10 +403,18 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
     // bandwidth: 96 B/cycle/SM instead of 128).  Estimate the tile count and take the widest tile whose last wave
     // is not mostly idle.
     const long long m_tiles_est = (args.M + 127) / 128 + (args.num_groups > 1 ? args.num_groups / 2 : 0);
+    const char* ts_env = getenv("VITA_B200_GEMM_TAIL_SPLIT");   // tuning aid: 0 switches the tail split off
+    const bool tail_split = !silu && !(ts_env && atoi(ts_env) == 0);
     auto wave_eff = [&](int bn_out) {
         const long long tiles = m_tiles_est * ((args.N + bn_out - 1) / bn_out);
-        const long long waves = (tiles + n_sms - 1) / n_sms;
-        return static_cast<double>(tiles) / static_cast<double>(waves * n_sms);
+        const long long whole = tiles / n_sms, rest = tiles % n_sms;
+        double waves = static_cast<double>(whole);
+        if (rest > 0) {
+            int sp = 1;
+            while (tail_split && sp < 4 && sp * 2 * rest <= n_sms) sp *= 2;
+            waves += 1.0 / sp;        // a piece of width 1/sp costs about 1/sp of a tile (HBM-bound) or a little more
+        }
+        return static_cast<double>(tiles) / (waves * n_sms);
     };
     int block_n;
     const char* force = getenv("VITA_B200_GEMM_BN");   // tuning aid: force the tile width (128 / 256)
@@ -373,7 +436,9 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
     const long long max_tiles_ll = m_tiles_ub * ((args.N + bn_out - 1) / bn_out);
     const int max_tiles = max_tiles_ll > (1 << 30) ? (1 << 30) : static_cast<int>(max_tiles_ll);
 
-    CUtensorMap tmA, tmB;
+    GemmArgs a2 = args;
+    a2.tail_split = tail_split ? 1 : 0;
+    CUtensorMap tmA, tmB, tmBs;
     {
         const uint64_t dims[2] = {static_cast<uint64_t>(args.K), static_cast<uint64_t>(a_rows)};
         const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
@@ -390,10 +455,20 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
         int rc = make_tensor_map_bf16(&tmB, B, 3, dims, strides, box, true);
         if (rc) return rc;
     }
-    if (silu && block_n == 256) return launch_gemm<256, true, 4>(tmA, tmB, args, max_tiles, stream);
-    if (silu) return launch_gemm<128, true, 6>(tmA, tmB, args, max_tiles, stream);
-    if (block_n == 256) return launch_gemm<256, false, 4>(tmA, tmB, args, max_tiles, stream);
-    return launch_gemm<128, false, 6>(tmA, tmB, args, max_tiles, stream);
+    tmBs = tmB;
+    if (tail_split) {
+        const uint64_t dims[3] = {static_cast<uint64_t>(args.K), static_cast<uint64_t>(b_rows),
+                                  static_cast<uint64_t>(args.num_groups)};
+        const uint64_t strides[2] = {static_cast<uint64_t>(args.K) * 2,
+                                     static_cast<uint64_t>(args.K) * 2 * static_cast<uint64_t>(b_rows)};
+        const uint32_t box[3] = {64, 32, 1};
+        int rc = make_tensor_map_bf16(&tmBs, B, 3, dims, strides, box, true);
+        if (rc) return rc;
+    }
+    if (silu && block_n == 256) return launch_gemm<256, true, 4>(tmA, tmB, tmBs, a2, max_tiles, stream);
+    if (silu) return launch_gemm<128, true, 6>(tmA, tmB, tmBs, a2, max_tiles, stream);
+    if (block_n == 256) return launch_gemm<256, false, 4>(tmA, tmB, tmBs, a2, max_tiles, stream);
+    return launch_gemm<128, false, 6>(tmA, tmB, tmBs, a2, max_tiles, stream);
 }
 
 }  // namespace vita

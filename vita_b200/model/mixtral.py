@@ -110,6 +110,10 @@ class MixtralDecoder:
         self._bgraphs = {}            # batched decode step: captured CUDA graph per batch size
         self.d_slots = torch.zeros(B, dtype=torch.int32, device=dev)
         self._prefill_ws = {}
+        # router decisions of every layer (the reference returns them as `router_logits` when asked,
+        # vita_mixtral.py:108,185-190): set to a list to have prefill() and the eager decode step append one
+        # (top-2 ids [T, 2] int32, renormalised weights [T, 2] fp32) pair per layer
+        self.route_trace: Optional[list] = None
         per = cfg.num_local_experts // self.ep_world
         self.e_lo, self.e_hi = self.ep_rank * per, (self.ep_rank + 1) * per
         assert weights["layers"][0]["w13"].shape[0] == per, "expert tensors do not match the EP layout"
@@ -255,6 +259,8 @@ class MixtralDecoder:
                           (0, nq * D, D), 1, nq, nkv, S, S, D, D, None, True, D ** -0.5)
             ops.linear(attn, lw["wo"], residual=h, out=h)
             ops.moe_router(h, lw["ln2"], lw["gate"], xn2, ids, tw, c.rms_norm_eps)
+            if self.route_trace is not None:
+                self.route_trace.append((ids.clone(), tw.clone()))
             ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, S, E, row_assign=ws["rassign"][:2 * S])
             ops.row_copy(xn2, rtok, None, xp, 2 * S)
             nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else (w["norm"] if all_logits else None)
@@ -402,6 +408,8 @@ class MixtralDecoder:
                 ops.decode_tc_oproj(self.d_attn[:B], lw["wo"], h, ws)
                 ops.decode_tc_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B],
                                           self.d_act[:B], ws, c.rms_norm_eps)
+                if self.route_trace is not None and not torch.cuda.is_current_stream_capturing():
+                    self.route_trace.append((self.d_ids[:B].clone(), self.d_w[:B].clone()))
                 ops.decode_tc_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h, ws)
             lg = self.d_logits[:B] if want_logits else None
             ops.tc_lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, ws, c.rms_norm_eps)
