@@ -235,12 +235,18 @@ int vita_decode_tc_qkv_rope(const void* h, const void* norm_w, const void* w_qkv
                             int64_t max_pages, float eps, void* stream);
 int vita_decode_tc_oproj(const void* x, const void* w, void* h, void* workspace, int64_t ws_row_blocks, int64_t B,
                          int64_t N, int64_t K, void* stream);
+/* route_word ([B] 64-bit words, or NULL) + route_tag (1 .. 2^32-1, different for neighbouring launches that share the
+ * word, e.g. layer index + 1): the gate|up kernel publishes {tag, e0, e1} as one word as soon as its router is done and
+ * triggers its dependent launch right then; the down projection given the same word and tag streams the rows of the
+ * selected experts into its shared-memory ring while the gate|up kernel is still running (it still waits for the
+ * activations).  NULL: the down projection reads topk_ids after its dependency wait. */
 int vita_decode_tc_moe_gate_up(const void* h, const void* norm_w, const void* gate_w, const void* w13,
                                int32_t* topk_ids, float* topk_w, void* act, void* workspace, int64_t ws_row_blocks,
-                               int64_t B, int64_t H, int64_t I, int64_t E, float eps, void* stream);
+                               int64_t B, int64_t H, int64_t I, int64_t E, float eps, uint64_t* route_word,
+                               int64_t route_tag, void* stream);
 int vita_decode_tc_moe_down(const void* act, const void* w2, const int32_t* topk_ids, const float* topk_w, void* h,
                             void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H, int64_t I, int64_t E,
-                            void* stream);
+                            const uint64_t* route_word, int64_t route_tag, void* stream);
 int vita_tc_lm_head_argmax(const void* h, int64_t h_stride, const void* norm_w, const void* w, void* logits,
                            uint64_t* best, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H, int64_t V,
                            float eps, void* stream);

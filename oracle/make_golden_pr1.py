@@ -191,7 +191,8 @@ def cmd_mint(args):
         top2_values=top2.values.numpy().astype(np.float32), top2_indices=top2.indices.numpy(),
         logit_rel_gaps=np.array(m["logit_rel_gaps"], dtype=np.float32),
         router_gaps=np.array(m["router_gaps"], dtype=np.float32),
-        first_row_head=rows[0, :4096].numpy().astype(np.float32), note=np.array(ref_note))
+        first_row_head=rows[0, :4096].numpy().astype(np.float32), note=np.array(ref_note),
+        gate_scale=np.float64(pr1.GATE_SCALE), head_gain_sigma=np.float64(pr1.HEAD_GAIN_SIGMA))
     print("[pr1] wrote", GOLDEN)
 
 

@@ -10,16 +10,21 @@ non-degenerate and a seed chosen once and recorded:
 
 * the lm_head rows get log-normal gains (sigma 2.5): heavy-tailed logits, the top-1 / top-2 gap is tens of percent of
   the top logit at most steps instead of 4 %;
-* the router weights are scaled x100 (std 2.0): the routing soft-max becomes sharp, so whenever the rank-2 and rank-3
-  experts are nearly tied (which random routers are at ~5 % of all decisions, whatever their scale) the second expert's
-  renormalised weight is tiny and swapping it for the third changes nothing measurable; a near-tie of the TOP two keeps
-  the expert set and moves the weights continuously.  Top-2 routing, renormalisation and both expert evaluations are
-  still exercised at every token;
+* the router weights are scaled x16 (a power of two: exact in bf16).  Two bf16 effects compete: a rank-2 / rank-3
+  near-tie flips an expert (frequency ~3 % of all decisions whatever the scale; harm = the second expert's weight, large
+  for soft routers), and the noise of the top-1 / top-2 logit difference moves the mixing weights (harm ~ scale).  Round 2
+  measured both ends on the GPU (profiles/r02_pr1_seed_search.json): x1 and x128 reproduce an fp32 trajectory less often
+  than x8 / x16, where a flipped second expert mostly carries a few percent of weight and the weight noise stays ~3 %;
 * everything else is `vita_b200.weights.synthetic_state` (std 0.02 matrices, 1 +- 0.1 norm gains), seed 0;
-* the prompt seed is searched (`make_golden_pr1.py search`) for a trajectory whose 33 logit rows are clear of near-ties
-  and whose router decisions (every layer, last prompt token and all generated tokens) are either clear (rank-2 vs
-  rank-3 gap above the bf16 noise of the two logits) or harmless (second weight <= 2 %); the chosen seed, the tokens and
-  the observed margins are recorded in tests/golden/pr1_l4.npz.
+* the prompt seed: `make_golden_pr1.py search` walks the seeds and keeps those whose 33 logit rows are clear of near-ties
+  (top-1 / top-2 gap >= 5 % of the top logit) and whose router decisions (every layer, last prompt token and all
+  generated tokens) are clear (rank-2 / rank-3 gap >= 2 % of the logits' spread) or harmless (second weight <= 2 %).
+  Of 300 seeds 5 qualify; the fixture uses the one with the widest router margin (seed 166: every such decision clear by
+  >= 12 % of the spread).  Even qualified seeds are not all reproducible in bf16 -- a flipped expert on a PROMPT token
+  changes that token's keys and values for every later query, and the criteria above cannot see it (4 of the other
+  qualified seeds diverge from the fp32 trajectory at some step, same file) -- which is why tests/test_pr1_gpu.py
+  also checks arbitrary seeds against the routing-aligned oracle.  The chosen seed, the tokens and the observed margins
+  are recorded in tests/golden/pr1_l4.npz.
 """
 from __future__ import annotations
 
@@ -35,7 +40,7 @@ PROMPT_LEN = 128
 NEW_TOKENS = 32
 WEIGHT_SEED = 0
 HEAD_GAIN_SIGMA = 2.5
-GATE_SCALE = 100.0
+GATE_SCALE = 16.0
 
 
 def config() -> VitaConfig:

@@ -17,13 +17,14 @@ from vita_b200.config import VitaConfig            # noqa: E402
 from vita_b200.model.mixtral import MixtralDecoder  # noqa: E402
 
 BASE = {"pdl": 1, "attn_early": 1, "attn_tagged": 1, "chain_wait": 1, "tc_prefetch_consts": 1, "tc_l2_ahead": 0,
-        "tc_trigger_lead": 0, "tc_wide_route": 1, "smem_carveout_max": 0, "chain_counters": 1}
+        "tc_trigger_lead": 0, "tc_wide_route": 1, "smem_carveout_max": 0, "chain_counters": 0}
 CONFIGS = {
     # name: (library options on top of BASE, decoder attributes)
     "nopdl": ({"pdl": 0}, {}),
     "default": ({}, {}),
-    "counters_off": ({"chain_counters": 0}, {}),
-    "counters_off_nopdl": ({"chain_counters": 0, "pdl": 0}, {}),
+    "counters_on": ({"chain_counters": 1}, {}),
+    "early_route_off": ({}, {"early_route": False}),
+    "early_route_lead4": ({"tc_trigger_lead": 4}, {}),
     "carveout_default": ({"smem_carveout_max": 0}, {}),
     "lead4": ({"tc_trigger_lead": 4}, {}),
     "l2a4": ({"tc_l2_ahead": 4}, {}),
@@ -53,7 +54,7 @@ def main():
         for n in names:
             opts, attrs = CONFIGS[n]
             opts = {**BASE, **opts}
-            attrs = {"decode_splits": 16, **attrs}
+            attrs = {"decode_splits": 16, "early_route": True, **attrs}
             for k, v in opts.items():
                 ops.set_option(k, v)
             for k, v in attrs.items():

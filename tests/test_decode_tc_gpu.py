@@ -187,3 +187,32 @@ def test_tc_tunables_keep_the_bits(tc_options):
     assert (tw - base[3]).abs().max() < 1e-5
     assert_close(act, base[1], rel=1e-3, what="narrow-router activations")
     assert_close(hd, base[0], rel=1e-3, what="narrow-router MoE output")
+
+
+def test_tc_early_route_handover_keeps_the_bits(tc_options):
+    """gate|up publishes the expert pair as one tagged word and the down projection streams its rows early: same bits as
+    the hand-over through topk_ids, with and without programmatic launch, over consecutive "layers" sharing the word."""
+    from vita_b200 import ops
+    B, H, I, E = 2, 4096, 14336, 8
+    nw, gw = to_dev(randn((H,), 2)), to_dev(randn((E, H), 3, 0.05))
+    w13, w2 = _gpu_randn((E, 2 * I, H), 4, 0.03), _gpu_randn((E, H, I), 5, 0.03)
+    ws = _ws(B, 2 * (I // 128))
+    hs = [to_dev(randn((B, H), 10 + i, 1.5)) for i in range(3)]
+    base = [_moe_pair(ops, h, nw, gw, w13, w2, ws, I) for h in hs]
+    word = torch.zeros(B, dtype=torch.int64, device="cuda")
+    for pdl in (1, 0):
+        tc_options("pdl", pdl)
+        for rep in range(2):
+            for layer, h in enumerate(hs):
+                hd = h.clone()
+                act = torch.empty(B, 2, I, dtype=BF16, device="cuda")
+                ids = torch.full((B, 2), -1, dtype=torch.int32, device="cuda")
+                tw = torch.zeros(B, 2, dtype=torch.float32, device="cuda")
+                ops.decode_tc_moe_gate_up(hd, nw, gw, w13, ids, tw, act, ws, 1e-5, word, layer + 1)
+                ops.decode_tc_moe_down(act, w2, ids, tw, hd, ws, word, layer + 1)
+                for a, b in zip(base[layer], (hd, act, ids, tw)):
+                    assert torch.equal(a, b), f"early route changed an output (pdl={pdl}, rep {rep}, layer {layer})"
+                w = word.cpu().tolist()
+                assert [x >> 32 for x in w] == [layer + 1] * B
+                assert [[(x >> 8) & 0xff, x & 0xff] for x in w] == ids.cpu().tolist()
+    tc_options("pdl", 1)

@@ -1,7 +1,14 @@
 """PR1 / BASELINE configs[0]: text-only Mixtral-8x7B geometry (full layer width, depth 4), 128-token prompt, bs = 1,
-32 FREE-RUNNING greedy tokens: every token id must equal the fp32 oracle's (which equals the reference's own classes,
-see the `note` field of the fixture) -- no margin gating, no teacher forcing.  The weight scaling and the prompt seed
-that make this well-posed are described in oracle/pr1.py; the fixture is minted by oracle/make_golden_pr1.py."""
+32 FREE-RUNNING greedy tokens.
+
+(1) Against the fixture minted from the reference's own classes (oracle/make_golden_pr1.py mint --reference): every token
+    id must equal the reference's -- no margin gating, no teacher forcing.  The weight scaling and the prompt seed that
+    make an fp32 trajectory reproducible in bf16 are described in oracle/pr1.py; profiles/r02_pr1_seed_search.json is
+    the search the seed came from.
+(2) For other prompt seeds, against the fp32 oracle run on the same GPU with the routing aligned (tests/full_depth.py):
+    every one of the 32 logits rows within tolerance and every id the oracle decides beyond that row's error equal.
+    This form holds for ANY seed: a random-init MoE turns a rank-2 / rank-3 router near-tie on a prompt token into a
+    different trajectory, which no bf16 implementation (the reference's own included) can avoid."""
 from pathlib import Path
 
 import numpy as np
@@ -13,19 +20,27 @@ pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden" / "pr1_l4.npz"
 
 
-@pytest.mark.skipif(not GOLDEN.exists(), reason="tests/golden/pr1_l4.npz not minted yet")
-def test_pr1_free_running_greedy_token_ids_exact():
+@pytest.fixture(scope="module")
+def pr1_model():
     from oracle import pr1
     from vita_b200 import weights as W
     from vita_b200.model.vita_mixtral import VITAMixtralForCausalLM
-    g = np.load(GOLDEN)
     cfg = pr1.config()
-    ids = pr1.prompt(int(g["prompt_seed"]), cfg.llm.vocab_size)
-    assert np.array_equal(ids.numpy(), g["input_ids"]), "prompt generator drifted from the fixture"
     state = pr1.build_state(cfg)
     model = VITAMixtralForCausalLM(cfg, {"llm": W.pack_llm(state, cfg, "cuda")}, "cuda", max_seq_len=256,
-                                   max_new_tokens=pr1.NEW_TOKENS)
+                                   max_new_tokens=pr1.NEW_TOKENS + 1)
     del state
+    return cfg, model
+
+
+@pytest.mark.skipif(not GOLDEN.exists(), reason="tests/golden/pr1_l4.npz not minted yet")
+def test_pr1_free_running_greedy_token_ids_exact(pr1_model):
+    from oracle import pr1
+    cfg, model = pr1_model
+    g = np.load(GOLDEN)
+    assert float(g["gate_scale"]) == pr1.GATE_SCALE, "fixture minted with another router scale"
+    ids = pr1.prompt(int(g["prompt_seed"]), cfg.llm.vocab_size)
+    assert np.array_equal(ids.numpy(), g["input_ids"]), "prompt generator drifted from the fixture"
     want = g["tokens"].tolist()
     out = model.generate(ids.cuda(), max_new_tokens=pr1.NEW_TOKENS, output_scores=True)
     got = out.sequences[0, pr1.PROMPT_LEN:].tolist()
@@ -41,3 +56,17 @@ def test_pr1_free_running_greedy_token_ids_exact():
     # CUDA-graph replay, eager launches and a different read-back cadence give the same ids
     again = model.generate(ids.cuda(), max_new_tokens=pr1.NEW_TOKENS, use_graph=False, sync_every=5)
     assert again.sequences[0, pr1.PROMPT_LEN:].tolist() == want
+
+
+@pytest.mark.parametrize("prompt_seed", [0, 1, 2])
+def test_pr1_any_seed_against_the_routing_aligned_oracle(pr1_model, prompt_seed):
+    from oracle import pr1
+    from tests.full_depth import check_mixtral
+    cfg, model = pr1_model
+    ids = pr1.prompt(prompt_seed, cfg.llm.vocab_size)
+    emb = model.packed["llm"]["embed"][ids[0].cuda()].contiguous()
+    r = check_mixtral(model, emb, n_tokens=pr1.NEW_TOKENS)
+    print({k: v for k, v in r.items() if k not in ("row_rel_err", "oracle_top2_rel_gap")})
+    assert r["max_row_rel_err"] < 4e-2, r                        # all 32 logits rows, depth 4
+    assert r["ids_equal_where_decided"] == r["ids_decided"] and r["ids_decided"] >= 16, r
+    assert r["routing_differ_frac"] < 0.06 and r["routing_weight_err_p99"] < 0.04, r

@@ -187,3 +187,32 @@ def test_whale_glue():
     xm = x.transpose(1, 2).masked_fill(~mask, 0.0)
     ref = F.conv1d(F.pad(xm, (0, 4)), wc, stride=2).transpose(1, 2)
     assert_close(y.view(B, T3, 2 * C), ref, rel=1e-4, what="whale adapter im2col")
+
+
+@pytest.mark.parametrize("T", [1, 7, 512, 513, 4096, 4600])
+def test_moe_align_is_a_stable_counting_sort(T):
+    from vita_b200 import ops
+    E = 8
+    g = torch.Generator().manual_seed(T)
+    ids_c = torch.stack([torch.randperm(E, generator=g)[:2] for _ in range(T)]).to(torch.int32)
+    if T > 100:
+        ids_c[T // 3: T // 2, 0] = 5          # a crowded expert and (below) an empty one
+        ids_c[ids_c == 2] = 6
+        ids_c[:, 1] = torch.where(ids_c[:, 1] == ids_c[:, 0], (ids_c[:, 0] + 1) % E, ids_c[:, 1])
+    tw_c = torch.rand(T, 2, generator=g)
+    ids, tw = ids_c.cuda(), tw_c.cuda()
+    offs = torch.empty(E + 1, dtype=torch.int32, device="cuda")
+    perm = torch.empty(T * 2, dtype=torch.int32, device="cuda")
+    rtok = torch.empty(T * 2, dtype=torch.int32, device="cuda")
+    rw = torch.empty(T * 2, dtype=torch.float32, device="cuda")
+    ra = torch.empty(T * 2, dtype=torch.int32, device="cuda")
+    ops.moe_align(ids, tw, offs, perm, rtok, rw, T, E, row_assign=ra)
+    flat = ids_c.reshape(-1).long()
+    assert offs.cpu().tolist() == [0] + torch.bincount(flat, minlength=E).cumsum(0).tolist()
+    order = torch.sort(flat, stable=True).indices
+    want_perm = torch.empty(T * 2, dtype=torch.long)
+    want_perm[order] = torch.arange(T * 2)
+    assert torch.equal(perm.cpu().long(), want_perm)
+    assert torch.equal(rtok.cpu().long(), order // 2)
+    assert torch.equal(ra.cpu().long(), order)
+    assert torch.equal(rw.cpu(), tw_c.reshape(-1)[order])

@@ -61,8 +61,8 @@ SIGNATURES = {
     "vita_decode_tc_workspace_bytes": (I64, [I64, I64]),
     "vita_decode_tc_qkv_rope": (c_int, [P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, c_float, P]),
     "vita_decode_tc_oproj": (c_int, [P, P, P, P, I64, I64, I64, I64, P]),
-    "vita_decode_tc_moe_gate_up": (c_int, [P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, c_float, P]),
-    "vita_decode_tc_moe_down": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, I64, P]),
+    "vita_decode_tc_moe_gate_up": (c_int, [P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, c_float, P, I64, P]),
+    "vita_decode_tc_moe_down": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, I64, P, I64, P]),
     "vita_tc_lm_head_argmax": (c_int, [P, I64, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
 }
 

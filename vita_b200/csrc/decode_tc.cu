@@ -315,13 +315,22 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer (weights)
             if (Op::kRowsNeedPrologue) mbar_wait(x_ready, 0, 21);      // expert ids computed by this CTA's prologue
-            else if (Op::kRowsNeedUpstream) chain_wait(chain);          // expert ids written by the previous kernel
+            else if (Op::kRowsNeedUpstream) {
+                // expert ids written by the previous kernel: either published early as one tagged word (then the
+                // weight rows stream while the predecessor is still running) or read after the dependency wait
+                if (!op.rows_from_route_word(b, sm)) {
+                    chain_wait(chain);
+                    op.rows_from_upstream(b, sm);
+                }
+            }
             int stage = 0;
             uint32_t phase = 0;
             // With programmatic dependent launch the next kernel of the chain may take the free half of the SM and fill
             // its ring while this CTA drains and reduces: trigger once all but `lead` of this CTA's loads are issued.
             // Waiting first (long since satisfied) makes the chain transitive: when kernel N+1 starts, N-1 is complete.
-            const int lead = flags >> 8;
+            // (an op that publishes its routing early triggers right away: its successor only needs the expert ids to
+            // start streaming, and those are out since this CTA's prologue)
+            const long long lead = op.trigger_at_start() ? (1ll << 60) : static_cast<long long>(flags >> 8);
             bool triggered = false;
             for (long long u = u0; u < u1; ++u) {
                 if (!triggered && u1 - u <= lead) {
@@ -330,6 +339,10 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
                     triggered = true;
                 }
                 const int rb = static_cast<int>(u / n_kb), kb = static_cast<int>(u % n_kb);
+                // ring full for the first time: nothing can drain it before the predecessor has completed (the
+                // activations come from it), so park on the hardware dependency instead of spinning on the barrier
+                // next to the predecessor's own producer / MMA threads
+                if (u - u0 == STAGES) chain_wait(chain);
                 mbar_wait(&empty_bar[stage], phase ^ 1, 22);
                 mbar_arrive_expect_tx(&full_bar[stage], STAGE_A);
 #pragma unroll
@@ -361,6 +374,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             long long u = u0;
+            chain_wait(chain);   // the activation vector derives from the predecessor: wait in hardware, not on full_bar
             while (u < u1) {
                 const int rb = static_cast<int>(u / n_kb);
                 long long seg_end = static_cast<long long>(rb + 1) * n_kb;
@@ -426,6 +440,8 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
                 }
             }
         } else {
+            if (lane == 0) chain_wait(chain);
+            __syncwarp();
             mbar_wait(x_ready, 0, 25);
             for (long long u = u0; u < u1; ++u) {
                 const int kb = static_cast<int>(u % n_kb);
@@ -568,6 +584,9 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
 
 // ------------------------------------------------------------------------------------------------ ops
 struct TcQkvOp {
+    __device__ bool rows_from_route_word(int, const TcSmem&) const { return false; }
+    __device__ void rows_from_upstream(int, const TcSmem&) const {}
+    __device__ bool trigger_at_start() const { return false; }
     static constexpr int kMaxRegs = 128;
     static constexpr int kId = 1;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
@@ -628,6 +647,9 @@ struct TcQkvOp {
 };
 
 struct TcOProjOp {
+    __device__ bool rows_from_route_word(int, const TcSmem&) const { return false; }
+    __device__ void rows_from_upstream(int, const TcSmem&) const {}
+    __device__ bool trigger_at_start() const { return false; }
     static constexpr int kMaxRegs = 128;
     static constexpr int kId = 3;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
@@ -673,14 +695,21 @@ struct TcGateUpOp {
     __nv_bfloat16* act;            // [B, 2, I]
     int K, I;
     float eps;
+    unsigned long long* route_word;   // [B] or nullptr: {tag, e0, e1} published as ONE word as soon as the router is done
+    unsigned int route_tag;
 
+    __device__ bool rows_from_route_word(int, const TcSmem&) const { return false; }
+    __device__ void rows_from_upstream(int, const TcSmem&) const {}
+    __device__ bool trigger_at_start() const { return route_word != nullptr; }
     __device__ int x_elems() const { return K; }
     __device__ int num_row_blocks() const { return 2 * (I / 128); }
     __device__ int a_row(int, int rb, int p, const TcSmem& sm) const {
         const int nb = I / 128, k = rb / nb, jb = rb % nb;
         return sm.misc[k] * 2 * I + p * I + jb * 128;   // rows of the fused [E * 2I, H] weight
     }
-    __device__ void pre_wait(int, const TcSmem&, bool on) const {
+    __device__ void pre_wait(int b, const TcSmem&, bool on) const {
+        // the word of the previous layer / step is dead by now (its reader completed before this kernel could start)
+        if (route_word != nullptr && blockIdx.x == 0 && threadIdx.x == 128) st_relaxed_u64(route_word + b, 0ull);
         if (!on) return;
         tc_prefetch_l2(gate_w, 8ll * K * 2);
         tc_prefetch_l2(norm_w, K * 2ll);
@@ -719,6 +748,10 @@ struct TcGateUpOp {
                 topk_ids[b * 2 + 1] = r.e1;
                 topk_w[b * 2] = r.w0;
                 topk_w[b * 2 + 1] = r.w1;
+                if (route_word != nullptr)
+                    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(route_word + b),
+                                 "l"((static_cast<unsigned long long>(route_tag) << 32) |
+                                     static_cast<unsigned long long>((r.e0 << 8) | r.e1)) : "memory");
             }
         }
         for (int i = t * 8; i < K; i += 128 * 8) {
@@ -753,11 +786,33 @@ struct TcDownOp {
     const float* topk_w;
     __nv_bfloat16* h;
     int K, H;                   // K = I
+    const unsigned long long* route_word;   // [B] or nullptr (see TcGateUpOp)
+    unsigned int route_tag;
 
+    // producer lane only: the expert ids of this token, from the word the gate|up kernel published early ...
+    __device__ bool rows_from_route_word(int b, const TcSmem& sm) const {
+        if (route_word == nullptr) return false;
+        for (int i = 0; i < 256; ++i) {   // published before this kernel could launch: the first load normally hits
+            unsigned long long w;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(route_word + b) : "memory");
+            if (static_cast<unsigned int>(w >> 32) == route_tag) {
+                sm.misc[0] = static_cast<int>((w >> 8) & 0xff);
+                sm.misc[1] = static_cast<int>(w & 0xff);
+                return true;
+            }
+        }
+        return false;
+    }
+    // ... or, after the dependency wait, from the ids array
+    __device__ void rows_from_upstream(int b, const TcSmem& sm) const {
+        sm.misc[0] = topk_ids[b * 2];
+        sm.misc[1] = topk_ids[b * 2 + 1];
+    }
+    __device__ bool trigger_at_start() const { return false; }
     __device__ int x_elems() const { return 0; }   // the activation vectors are streamed from L2 by the x-tile writer
     __device__ const __nv_bfloat16* x_global(int b) const { return act + static_cast<long long>(b) * 2 * K; }
     __device__ int num_row_blocks() const { return (H + 127) / 128; }
-    __device__ int a_row(int b, int rb, int p, const TcSmem&) const { return topk_ids[b * 2 + p] * H + rb * 128; }
+    __device__ int a_row(int, int rb, int p, const TcSmem& sm) const { return sm.misc[p] * H + rb * 128; }
     __device__ void pre_wait(int, const TcSmem&, bool) const {}
     __device__ void wide_partials(int, const TcSmem&) const {}
     __device__ void prologue(int b, const TcSmem& sm, bool) const {
@@ -782,6 +837,9 @@ __device__ __forceinline__ unsigned long long tc_pack_argmax(float v, int idx) {
 }
 
 struct TcLmHeadOp {
+    __device__ bool rows_from_route_word(int, const TcSmem&) const { return false; }
+    __device__ void rows_from_upstream(int, const TcSmem&) const {}
+    __device__ bool trigger_at_start() const { return false; }
     static constexpr int kMaxRegs = 128;
     static constexpr int kId = 6;
     __device__ const __nv_bfloat16* x_global(int) const { return nullptr; }
@@ -930,26 +988,33 @@ extern "C" int vita_decode_tc_oproj(const void* x, const void* w, void* h, void*
 extern "C" int vita_decode_tc_moe_gate_up(const void* h, const void* norm_w, const void* gate_w, const void* w13,
                                           int32_t* topk_ids, float* topk_w, void* act, void* workspace,
                                           int64_t ws_row_blocks, int64_t B, int64_t H, int64_t I, int64_t E, float eps,
-                                          void* stream) {
+                                          uint64_t* route_word, int64_t route_tag, void* stream) {
     VITA_REQUIRE(E == 8, "router is specialised for 8 experts (Mixtral-8x7B)");
     VITA_REQUIRE(tc_shape_ok(H) && I % 128 == 0, "H must be a multiple of 64 and I a multiple of 128");
     const int n_rb = static_cast<int>(2 * (I / 128));
     VITA_REQUIRE(workspace && n_rb <= ws_row_blocks, "workspace too small");
     if (B == 0) return VITA_OK;
+    VITA_REQUIRE(route_word == nullptr || (route_tag > 0 && route_tag < (1ll << 32)), "route_tag must be in [1, 2^32)");
+    // the early hand-over relies on the chain being transitive (option chain_wait) -- otherwise it stays off
+    unsigned long long* rw = option("chain_wait") ? reinterpret_cast<unsigned long long*>(route_word) : nullptr;
     TcGateUpOp op{BF16C(h), BF16C(norm_w), BF16C(gate_w), topk_ids, topk_w, static_cast<__nv_bfloat16*>(act), (int)H,
-                  (int)I, eps};
+                  (int)I, eps, rw, static_cast<unsigned int>(route_tag)};
     return launch_tc(op, w13, E * 2 * I, (int)H, n_rb, (int)H, (int)B, split_ws(workspace, B, ws_row_blocks),
                      static_cast<cudaStream_t>(stream), "decode_tc_moe_gate_up");
 }
 
 extern "C" int vita_decode_tc_moe_down(const void* act, const void* w2, const int32_t* topk_ids, const float* topk_w,
                                        void* h, void* workspace, int64_t ws_row_blocks, int64_t B, int64_t H,
-                                       int64_t I, int64_t E, void* stream) {
+                                       int64_t I, int64_t E, const uint64_t* route_word, int64_t route_tag,
+                                       void* stream) {
     VITA_REQUIRE(tc_shape_ok(I) && H % 128 == 0, "I must be a multiple of 64 and H a multiple of 128");
     const int n_rb = static_cast<int>(H / 128);
     VITA_REQUIRE(workspace && n_rb <= ws_row_blocks, "workspace too small");
     if (B == 0) return VITA_OK;
-    TcDownOp op{BF16C(act), topk_ids, topk_w, static_cast<__nv_bfloat16*>(h), (int)I, (int)H};
+    VITA_REQUIRE(route_word == nullptr || (route_tag > 0 && route_tag < (1ll << 32)), "route_tag must be in [1, 2^32)");
+    const unsigned long long* rw = option("chain_wait") ? reinterpret_cast<const unsigned long long*>(route_word) : nullptr;
+    TcDownOp op{BF16C(act), topk_ids, topk_w, static_cast<__nv_bfloat16*>(h), (int)I, (int)H, rw,
+                static_cast<unsigned int>(route_tag)};
     return launch_tc(op, w2, E * H, (int)I, n_rb, 0, (int)B, split_ws(workspace, B, ws_row_blocks),
                      static_cast<cudaStream_t>(stream), "decode_tc_moe_down");
 }

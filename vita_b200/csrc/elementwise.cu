@@ -328,6 +328,75 @@ moe_align_kernel(const int* __restrict__ topk_ids, const float* __restrict__ top
     }
 }
 
+// E <= 8: every thread owns a contiguous chunk of the assignments (so the order inside an expert stays the assignment
+// order), counts its chunk per expert, the block scans the counts (warp shuffles + one smem level), and the thread walks
+// its chunk a second time handing out rows.  Two passes over 8 items per thread at S = 4096 instead of 256 ballot rounds
+// per warp (56 us -> a few us per layer).
+__global__ void __launch_bounds__(1024)
+moe_align8_kernel(const int* __restrict__ topk_ids, const float* __restrict__ topk_w, int* __restrict__ expert_offsets,
+                  int* __restrict__ perm_row, int* __restrict__ row_token, float* __restrict__ row_weight,
+                  int* __restrict__ row_assign, int n_assign, int E) {
+    __shared__ int warp_tot[32][8];
+    __shared__ int base[9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ipt = (n_assign + 1023) >> 10;
+    const int i0 = threadIdx.x * ipt, i1 = min(n_assign, i0 + ipt);
+    int cnt[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cnt[e] = 0;
+    for (int i = i0; i < i1; ++i) {
+        const int id = topk_ids[i];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cnt[e] += (id == e);
+    }
+    int pre[8];   // exclusive prefix of this thread inside the block, per expert
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int v = cnt[e];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        pre[e] = v - cnt[e];
+        if (lane == 31) warp_tot[warp][e] = v;
+    }
+    __syncthreads();
+    if (warp < 8) {   // warp e scans the 32 warp totals of expert e
+        const int t = warp_tot[lane][warp];
+        int v = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        warp_tot[lane][warp] = v - t;          // exclusive prefix of the warp
+        if (lane == 31) base[warp] = v;        // total of the expert (turned into its first row below)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int e = 0; e < 8; ++e) { const int c = base[e]; base[e] = acc; acc += c; }
+        base[8] = acc;
+        for (int e = 0; e <= E; ++e) expert_offsets[e] = base[e < 8 ? e : 8];
+    }
+    __syncthreads();
+    int nxt[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) nxt[e] = base[e] + warp_tot[warp][e] + pre[e];
+    for (int i = i0; i < i1; ++i) {
+        const int id = topk_ids[i];
+        int r = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (id == e) { r = nxt[e]; nxt[e] = r + 1; }
+        perm_row[i] = r;
+        row_token[r] = i >> 1;
+        row_weight[r] = topk_w[i];
+        if (row_assign) row_assign[r] = i;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ MoE combine
 // MixtralExperts.forward index_add_ (modeling_mixtral.py:96) + the decoder-layer residual add, optionally followed
 // by the next RMSNorm (next layer's input_layernorm or the final norm) so the residual stream is read once.
@@ -782,9 +851,14 @@ extern "C" int vita_moe_align(const int32_t* topk_ids, const float* topk_w, int3
                               int32_t* perm_row, int32_t* row_token, float* row_weight, int32_t* row_assign,
                               int64_t n_tok, int64_t E, void* stream) {
     VITA_REQUIRE(E >= 1 && E <= 32, "E must be in [1, 32]");
-    moe_align_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(topk_ids, topk_w, expert_offsets, perm_row,
-                                                                        row_token, row_weight, row_assign,
-                                                                        (int)(n_tok * 2), (int)E);
+    if (E <= 8)
+        moe_align8_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(topk_ids, topk_w, expert_offsets, perm_row,
+                                                                             row_token, row_weight, row_assign,
+                                                                             (int)(n_tok * 2), (int)E);
+    else
+        moe_align_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(topk_ids, topk_w, expert_offsets, perm_row,
+                                                                            row_token, row_weight, row_assign,
+                                                                            (int)(n_tok * 2), (int)E);
     return check_launch("moe_align");
 }
 

@@ -405,16 +405,21 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
     const long long m_tiles_est = (args.M + 127) / 128 + (args.num_groups > 1 ? args.num_groups / 2 : 0);
     const char* ts_env = getenv("VITA_B200_GEMM_TAIL_SPLIT");   // tuning aid: 0 switches the tail split off
     const bool tail_split = !silu && !(ts_env && atoi(ts_env) == 0);
-    auto wave_eff = [&](int bn_out) {
-        const long long tiles = m_tiles_est * ((args.N + bn_out - 1) / bn_out);
+    // Estimated duration in units of one 128 x 256 tile on one SM.  Measured on B200 (profiles/r02_gemm_shapes.txt):
+    // a 128-wide tile costs 0.76 of a 256-wide one when compute-bound (its A operand is read twice as often per flop),
+    // half when the weights are streamed once from HBM (few row tiles); the pieces of a cut tail tile likewise
+    // 0.75 / 0.6 of the whole for 1/2 and 1/4 of the width when compute-bound, 1/2 and 1/4 when HBM-bound.
+    const bool hbm_bound = m_tiles_est <= 2;
+    auto est_time = [&](int bn) {
+        const long long tiles = m_tiles_est * ((args.N + bn - 1) / bn);
         const long long whole = tiles / n_sms, rest = tiles % n_sms;
         double waves = static_cast<double>(whole);
         if (rest > 0) {
             int sp = 1;
             while (tail_split && sp < 4 && sp * 2 * rest <= n_sms) sp *= 2;
-            waves += 1.0 / sp;        // a piece of width 1/sp costs about 1/sp of a tile (HBM-bound) or a little more
+            waves += hbm_bound ? 1.0 / sp : (sp == 1 ? 1.0 : (sp == 2 ? 0.75 : 0.6));
         }
-        return static_cast<double>(tiles) / (waves * n_sms);
+        return waves * (bn == 256 ? 1.0 : (hbm_bound ? 0.5 : 0.76));
     };
     int block_n;
     const char* force = getenv("VITA_B200_GEMM_BN");   // tuning aid: force the tile width (128 / 256)
@@ -427,10 +432,8 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
         block_n = 256;
     } else if (args.N < 256) {
         block_n = 128;
-    } else if (m_tiles_est * ((args.N + 255) / 256) >= 2 * n_sms) {
-        block_n = 256;   // many tiles: compute-bound, the wide tile wins (measured 1234 vs 891 TFLOP/s at M=4096)
     } else {
-        block_n = (wave_eff(256) + 0.04 >= wave_eff(128)) ? 256 : 128;
+        block_n = (est_time(256) <= est_time(128) * 1.02) ? 256 : 128;
     }
     const int bn_out = silu ? block_n / 2 : block_n;
     const long long max_tiles_ll = m_tiles_ub * ((args.N + bn_out - 1) / bn_out);

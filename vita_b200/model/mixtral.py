@@ -94,6 +94,7 @@ class MixtralDecoder:
         self.d_xn = torch.zeros(B, H, dtype=BF16, device=dev)
         self.d_ids = torch.zeros(B, 2, dtype=torch.int32, device=dev)
         self.d_w = torch.zeros(B, 2, dtype=torch.float32, device=dev)
+        self.d_route = torch.zeros(B, dtype=torch.int64, device=dev)      # early routing hand-over gate|up -> down
         self.d_act = torch.zeros(B, 2, I, dtype=BF16, device=dev)
         self.d_logits = torch.zeros(B, cfg.vocab_size, dtype=BF16, device=dev)
         self.attn_ws = ops.decode_attention_workspace(B, cfg.num_key_value_heads, self.decode_splits, dev)
@@ -114,6 +115,9 @@ class MixtralDecoder:
         # vita_mixtral.py:108,185-190): set to a list to have prefill() and the eager decode step append one
         # (top-2 ids [T, 2] int32, renormalised weights [T, 2] fp32) pair per layer
         self.route_trace: Optional[list] = None
+        # decode: the gate|up kernel publishes the expert pair as soon as its router is done and the down projection
+        # streams its weight rows while gate|up is still running (VITA_B200_EARLY_ROUTE=0 switches the hand-over off)
+        self.early_route = os.environ.get("VITA_B200_EARLY_ROUTE", "1") == "1"
         per = cfg.num_local_experts // self.ep_world
         self.e_lo, self.e_hi = self.ep_rank * per, (self.ep_rank + 1) * per
         assert weights["layers"][0]["w13"].shape[0] == per, "expert tensors do not match the EP layout"
@@ -406,11 +410,13 @@ class MixtralDecoder:
                                      self.d_attn[:B], self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits,
                                      D ** -0.5)
                 ops.decode_tc_oproj(self.d_attn[:B], lw["wo"], h, ws)
+                tracing = self.route_trace is not None and not torch.cuda.is_current_stream_capturing()
+                route = None if (tracing or not self.early_route) else self.d_route[:B]
                 ops.decode_tc_moe_gate_up(h, lw["ln2"], lw["gate"], lw["w13"], self.d_ids[:B], self.d_w[:B],
-                                          self.d_act[:B], ws, c.rms_norm_eps)
-                if self.route_trace is not None and not torch.cuda.is_current_stream_capturing():
+                                          self.d_act[:B], ws, c.rms_norm_eps, route, li + 1)
+                if tracing:
                     self.route_trace.append((self.d_ids[:B].clone(), self.d_w[:B].clone()))
-                ops.decode_tc_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h, ws)
+                ops.decode_tc_moe_down(self.d_act[:B], lw["w2"], self.d_ids[:B], self.d_w[:B], h, ws, route, li + 1)
             lg = self.d_logits[:B] if want_logits else None
             ops.tc_lm_head_argmax(h, c.hidden_size, w["norm"], w["lm_head"], lg, self.best[:B], B, ws, c.rms_norm_eps)
         finally:

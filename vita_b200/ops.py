@@ -342,16 +342,18 @@ def decode_tc_oproj(x, w, h, ws):
     _lib.call("vita_decode_tc_oproj", _p(x), _p(w), _p(h), _p(ws.buf), ws.max_row_blocks, B, N, w.shape[1], _stream())
 
 
-def decode_tc_moe_gate_up(h, norm_w, gate_w, w13, topk_ids, topk_w, act, ws, eps):
+def decode_tc_moe_gate_up(h, norm_w, gate_w, w13, topk_ids, topk_w, act, ws, eps, route_word=None, route_tag=0):
+    """`route_word` ([B] int64) + `route_tag` (>= 1): publish the routing early for decode_tc_moe_down (see the header)."""
     B, H = h.shape
     _lib.call("vita_decode_tc_moe_gate_up", _p(h), _p(norm_w), _p(gate_w), _p(w13), _p(topk_ids), _p(topk_w), _p(act),
-              _p(ws.buf), ws.max_row_blocks, B, H, w13.shape[1] // 2, gate_w.shape[0], float(eps), _stream())
+              _p(ws.buf), ws.max_row_blocks, B, H, w13.shape[1] // 2, gate_w.shape[0], float(eps), _p(route_word),
+              int(route_tag), _stream())
 
 
-def decode_tc_moe_down(act, w2, topk_ids, topk_w, h, ws):
+def decode_tc_moe_down(act, w2, topk_ids, topk_w, h, ws, route_word=None, route_tag=0):
     B, H = h.shape
     _lib.call("vita_decode_tc_moe_down", _p(act), _p(w2), _p(topk_ids), _p(topk_w), _p(h), _p(ws.buf),
-              ws.max_row_blocks, B, H, w2.shape[2], w2.shape[0], _stream())
+              ws.max_row_blocks, B, H, w2.shape[2], w2.shape[0], _p(route_word), int(route_tag), _stream())
 
 
 def tc_lm_head_argmax(h, h_stride, norm_w, w, logits, best, B, ws, eps):
