@@ -562,7 +562,7 @@ def run_b200(args):
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gu_bytes / 1e9 / (gu_ms / 1e3) / pk["hbm_gbs"],
                          "traffic": ncu_traffic_bytes(roof_kernel), "bytes_per_launch": gu_bytes,
                          "us_per_launch": gu_ms * 1e3, "peak_source": pk["source"],
-                         "traffic_source": "profiles/r01_prof_tc_gateup_full.md (ncu --set full, one launch, "
+                         "traffic_source": "profiles/r02_prof_tc_gateup_full.md (ncu --set full, one launch, "
                                            "dram__bytes_read.sum + dram__bytes_write.sum)"},
             "prefill_long": None if long_ms is None else {
                 "S": S_LONG, "ms": long_ms, "tflops": prefill_flops(S_LONG, cfg) / (long_ms / 1e3) / 1e12,
@@ -629,7 +629,7 @@ def run_b200(args):
 def ncu_traffic_bytes(kernel_name: str):
     """DRAM bytes of one launch of the roofline kernel, from the committed ncu --set full summary (None if the active
     decode path is not the profiled kernel or the summary is missing)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_prof_tc_gateup_full.md")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_prof_tc_gateup_full.md")
     if "TcGateUpOp" not in kernel_name or not os.path.exists(path):
         return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

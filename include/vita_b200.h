@@ -82,6 +82,15 @@ int vita_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_
                        void* k_cache, void* v_cache, int64_t n_tok, int64_t n_q_heads, int64_t n_kv_heads,
                        int64_t head_dim, void* stream);
 
+/* The qkv projection with both of the above in its epilogue: qkv_out[M, (n_q + 2 n_kv) * 128] = X[M, K] . W_qkv^T, the
+ * q and k heads rotated with positions[row] (on the bf16-rounded projections, bit-identical to vita_gemm_bf16 followed
+ * by vita_rope_kv_write), k / v heads also stored at slot_mapping[row] of the paged caches (NULL = no cache write).
+ * Replaces q_proj/k_proj/v_proj + apply_rotary_pos_emb + the cache update of MixtralAttention.forward
+ * (modeling_mixtral.py:312-340; vLLM twin mixtral.py:470-501). */
+int vita_gemm_qkv_rope(const void* X, int64_t ldx, const void* W_qkv, void* qkv_out, int64_t M, int64_t K,
+                       int64_t n_q_heads, int64_t n_kv_heads, int64_t head_dim, const int32_t* positions,
+                       const int32_t* slot_mapping, const float* cos_sin, void* k_cache, void* v_cache, void* stream);
+
 /* ---- attention -------------------------------------------------------------------------------------------- */
 /* softmax(Q K^T * scale [causal] [kv_lens mask]) V, FlashAttention style.  Strides are {batch, token, head} in
  * elements.  Supported (d_qk, d_v): (128,128) Mixtral GQA, (64,64) InternViT, (128,64) Whale rel-pos with the
@@ -123,6 +132,21 @@ int vita_moe_gemm_down(const void* Act, const void* W_down, void* Y_perm, const 
                        const float* row_weight, int64_t rows, int64_t num_experts, int64_t H, int64_t I, void* stream);
 /* h[t] += Y_perm[perm_row[t,0]] + Y_perm[perm_row[t,1]] (index_add_ + residual, modeling_mixtral.py:96,386-389);
  * if next_norm_w != NULL also writes xn_out = RMSNorm(h) for the next layer / final norm. */
+/* Fused top-2 router + token permute ("slot" layout): as vita_moe_router, but instead of xn / an offsets pass / a gather
+ * pass the CTA of a token claims one row in each of its two experts' slot ranges (expert e owns rows [e * capacity,
+ * (e + 1) * capacity) of x_slots; expert_counts[e], zero on entry, counts the claimed rows) and stores the normed
+ * activations there; perm_row[t, k] = the claimed row, row_weight[row] = the renormalised routing weight.  topk_ids /
+ * topk_w (optional) as vita_moe_router.  The grouped GEMMs *_slots walk the same layout; vita_moe_combine gathers by
+ * perm_row.  Row order inside an expert is arrival order; results do not depend on it (rows are independent). */
+int vita_moe_route_scatter(const void* h, const void* norm_w, const void* gate_w, void* x_slots, int32_t* expert_counts,
+                           int32_t* perm_row, float* row_weight, int32_t* topk_ids, float* topk_w, int64_t n_tok,
+                           int64_t H, int64_t E, int64_t capacity, float eps, void* stream);
+int vita_moe_gemm_gate_up_silu_slots(const void* X_slots, const void* W_gate_up, void* Act_slots,
+                                     const int32_t* expert_counts, int64_t capacity, int64_t rows_hint,
+                                     int64_t num_experts, int64_t H, int64_t I, void* stream);
+int vita_moe_gemm_down_slots(const void* Act_slots, const void* W_down, void* Y_slots, const int32_t* expert_counts,
+                             const float* row_weight, int64_t capacity, int64_t rows_hint, int64_t num_experts, int64_t H,
+                             int64_t I, void* stream);
 int vita_moe_combine(void* h, const void* y_perm, const int32_t* perm_row, const void* next_norm_w, void* xn_out,
                      int64_t n_tok, int64_t H, float eps, void* stream);
 

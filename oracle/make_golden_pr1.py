@@ -53,7 +53,11 @@ def oracle_greedy(state, cfg, ids, n_new):
 
 def cmd_search(args):
     """For every router scale in --scales (powers of two: exact in bf16) walk the prompt seeds, compute the oracle's
-    trajectory and margins, and run the CUDA path on every seed whose logit margins qualify."""
+    trajectory and margins, and run the CUDA path on every seed whose logit margins qualify -- first as shipped, then
+    (if that reproduces the 32 tokens) in numerically distinct variants of itself: exp2 without the polynomial chunk,
+    the narrow router summation order, a cos/sin table computed by another libm.  A seed that survives all of them is
+    reproducible at bf16 precision for a reason (its decisions have real margins), not by a coin flip: a random-init MoE
+    turns an ulp into another trajectory at most seeds (profiles/r02_pr1_seed_search.json)."""
     on_gpu = torch.cuda.is_available()      # a GPU makes a candidate cost ~0.2 s instead of ~35 s; the CPU works too
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
@@ -62,23 +66,45 @@ def cmd_search(args):
     state_bf16 = pr1.build_state(cfg, gate_scale=1.0)
     print(f"[pr1] state built in {time.time() - t0:.0f}s", flush=True)
     dev = "cuda" if on_gpu else "cpu"
+    model = ops = None
+    variants = []
     if on_gpu:
-        torch.set_default_device("cuda")
+        # the CUDA path exactly as tests/test_pr1_gpu.py builds it (host-computed rope table, default options)
+        from vita_b200 import ops, weights as W
+        from vita_b200.model.vita_mixtral import VITAMixtralForCausalLM
+        model = VITAMixtralForCausalLM(cfg, {"llm": W.pack_llm(state_bf16, cfg, "cuda")}, "cuda", max_seq_len=256,
+                                       max_new_tokens=pr1.NEW_TOKENS + 1)
+        rope_host = model.llm.w["rope"].clone()
+        with torch.device("cuda"):
+            rope_dev = W.rope_table(rope_host.shape[0], cfg.llm.head_dim, cfg.llm.rope_theta)
+        print(f"[pr1] rope table host vs device libm: max |diff| {(rope_host - rope_dev).abs().max().item():.2e}", flush=True)
+
+        def variant(name, opts=None, rope=None):
+            def run(ids_cpu):
+                for k, v in (opts or {}).items():
+                    ops.set_option(k, v)
+                if rope is not None:
+                    model.llm.w["rope"].copy_(rope)
+                model.llm._graphs = {}
+                try:
+                    return model.generate(ids_cpu.cuda(), max_new_tokens=pr1.NEW_TOKENS, output_scores=True) \
+                        .sequences[0, pr1.PROMPT_LEN:].tolist()
+                finally:
+                    for k in (opts or {}):
+                        ops.set_option(k, DEFAULTS[k])
+                    model.llm.w["rope"].copy_(rope_host)
+                    model.llm._graphs = {}
+            return name, run
+        DEFAULTS = {k: ops.get_option(k) for k in ("fa_poly", "tc_wide_route")}
+        variants = [variant("as_shipped"), variant("exp2_mufu_only", {"fa_poly": 0}),
+                    variant("narrow_router", {"tc_wide_route": 0}), variant("device_rope_table", rope=rope_dev),
+                    variant("all_three", {"fa_poly": 0, "tc_wide_route": 0}, rope_dev)]
         state = {k: v.to("cuda").float() for k, v in state_bf16.items()}
     else:
         state = {k: v.clone() for k, v in state_bf16.items()}
-    model = None
-    try:
-        if not on_gpu:
-            raise RuntimeError("no GPU: margins only")
-        from vita_b200 import weights as W
-        from vita_b200.model.vita_mixtral import VITAMixtralForCausalLM
-        model = VITAMixtralForCausalLM(cfg, {"llm": W.pack_llm(state_bf16, cfg, "cuda")}, "cuda", max_seq_len=256,
-                                       max_new_tokens=pr1.NEW_TOKENS)
-    except Exception as e:   # pragma: no cover
-        print("[pr1] CUDA path unavailable:", e, flush=True)
     gkeys = [f"model.layers.{l}.block_sparse_moe.gate.weight" for l in range(cfg.llm.num_hidden_layers)]
-    out = {"criteria": {"logit_rel_gap_min": LOGIT_GAP_MIN, "router_gap_min": ROUTER_GAP_MIN}, "scales": {}}
+    out = {"criteria": {"logit_rel_gap_min": LOGIT_GAP_MIN, "router_gap_min": ROUTER_GAP_MIN},
+           "variants": [v[0] for v in variants], "scales": {}}
     cur = 1.0
     for scale in [float(x) for x in args.scales.split(",")]:
         f = scale / cur
@@ -89,10 +115,11 @@ def cmd_search(args):
                 model.packed["llm"]["layers"][l]["gate"].mul_(f)
         cur = scale
         gnorms = pr1.gate_norms(state_bf16, cfg)
-        cands, n_ok, n_run, n_eq = [], 0, 0, 0
+        cands, n_ok, n_run, n_eq, n_robust = [], 0, 0, 0, 0
         for seed in range(args.first, args.max):
-            ids = pr1.prompt(seed, cfg.llm.vocab_size).to(dev)
-            toks, rows, probs = oracle_greedy(state, cfg, ids, pr1.NEW_TOKENS)
+            ids_cpu = pr1.prompt(seed, cfg.llm.vocab_size)
+            with torch.device(dev):
+                toks, rows, probs = oracle_greedy(state, cfg, ids_cpu.to(dev), pr1.NEW_TOKENS)
             m = pr1.margins(rows.cpu(), [[p.cpu() for p in s] for s in probs], gnorms, cfg.llm.hidden_size)
             logit_ok = m["logit_rel_gap_min"] >= LOGIT_GAP_MIN
             ok = logit_ok and m["router_gap_min"] >= ROUTER_GAP_MIN
@@ -100,24 +127,28 @@ def cmd_search(args):
                    "router_gap_min": m["router_gap_min"], "weight_noise_max": m["weight_noise_max"], "ok": ok,
                    "tokens": toks, "distinct_tokens": len(set(toks))}
             if model is not None and logit_ok:
-                with torch.device("cpu"):
-                    got = model.generate(ids.cpu(), max_new_tokens=pr1.NEW_TOKENS).sequences[0, pr1.PROMPT_LEN:].tolist()
-                rec["cuda_tokens_equal"] = got == toks
-                rec["cuda_first_diff"] = next((i for i, (a, b) in enumerate(zip(got, toks)) if a != b), None)
-                if rec["cuda_first_diff"] is not None:
-                    rec["gap_at_first_diff"] = m["logit_rel_gaps"][rec["cuda_first_diff"]]
+                res = {}
+                for name, run in variants:
+                    got = run(ids_cpu)
+                    res[name] = next((i for i, (a, b) in enumerate(zip(got, toks)) if a != b), None)
+                    if name == "as_shipped" and res[name] is not None:
+                        break                                   # not reproducible as shipped: no need for the variants
+                rec["first_diff_by_variant"] = res
+                rec["cuda_tokens_equal"] = res["as_shipped"] is None
+                rec["robust"] = len(res) == len(variants) and all(v is None for v in res.values())
                 n_run += 1
                 n_eq += rec["cuda_tokens_equal"]
+                n_robust += rec["robust"]
             if logit_ok or not on_gpu:
                 cands.append(rec)
                 print(f"[pr1] scale {scale:g}", json.dumps({k: v for k, v in rec.items() if k != "tokens"}), flush=True)
             n_ok += ok
-            if n_ok >= args.want:
+            if n_robust >= args.want:
                 break
         out["scales"][f"{scale:g}"] = {"candidates": cands, "seeds_tried": seed + 1 - args.first,
-                                       "cuda_runs": n_run, "cuda_equal": n_eq}
+                                       "cuda_runs": n_run, "cuda_equal": n_eq, "cuda_robust": n_robust}
         print(f"[pr1] scale {scale:g}: {n_ok} margin-qualified seed(s) in {seed + 1 - args.first}; CUDA path equal on "
-              f"{n_eq} of {n_run} logit-qualified seeds, {time.time() - t0:.0f}s", flush=True)
+              f"{n_eq} of {n_run} logit-qualified seeds, in every variant on {n_robust}, {time.time() - t0:.0f}s", flush=True)
     Path("gpurun_out").mkdir(exist_ok=True)
     Path(f"gpurun_out/pr1_search{'' if on_gpu else '_cpu'}.json").write_text(json.dumps(out, indent=1))
 

@@ -10,21 +10,22 @@ non-degenerate and a seed chosen once and recorded:
 
 * the lm_head rows get log-normal gains (sigma 2.5): heavy-tailed logits, the top-1 / top-2 gap is tens of percent of
   the top logit at most steps instead of 4 %;
-* the router weights are scaled x16 (a power of two: exact in bf16).  Two bf16 effects compete: a rank-2 / rank-3
+* the router weights are scaled x8 (a power of two: exact in bf16).  Two bf16 effects compete: a rank-2 / rank-3
   near-tie flips an expert (frequency ~3 % of all decisions whatever the scale; harm = the second expert's weight, large
   for soft routers), and the noise of the top-1 / top-2 logit difference moves the mixing weights (harm ~ scale).  Round 2
   measured both ends on the GPU (profiles/r02_pr1_seed_search.json): x1 and x128 reproduce an fp32 trajectory less often
-  than x8 / x16, where a flipped second expert mostly carries a few percent of weight and the weight noise stays ~3 %;
+  than x8 / x16, where a flipped second expert mostly carries a few percent of weight and the weight noise stays ~1.5 %;
 * everything else is `vita_b200.weights.synthetic_state` (std 0.02 matrices, 1 +- 0.1 norm gains), seed 0;
-* the prompt seed: `make_golden_pr1.py search` walks the seeds and keeps those whose 33 logit rows are clear of near-ties
-  (top-1 / top-2 gap >= 5 % of the top logit) and whose router decisions (every layer, last prompt token and all
-  generated tokens) are clear (rank-2 / rank-3 gap >= 2 % of the logits' spread) or harmless (second weight <= 2 %).
-  Of 300 seeds 5 qualify; the fixture uses the one with the widest router margin (seed 166: every such decision clear by
-  >= 12 % of the spread).  Even qualified seeds are not all reproducible in bf16 -- a flipped expert on a PROMPT token
-  changes that token's keys and values for every later query, and the criteria above cannot see it (4 of the other
-  qualified seeds diverge from the fp32 trajectory at some step, same file) -- which is why tests/test_pr1_gpu.py
-  also checks arbitrary seeds against the routing-aligned oracle.  The chosen seed, the tokens and the observed margins
-  are recorded in tests/golden/pr1_l4.npz.
+* the prompt seed: `make_golden_pr1.py search` walks the seeds, keeps those whose 33 logit rows are clear of near-ties
+  (top-1 / top-2 gap >= 5 % of the top logit) and runs the CUDA path on them -- as shipped and in four numerically
+  distinct variants of itself (exp2 without the polynomial chunk, the narrow router summation order, a cos/sin table
+  from another libm, all three).  A random-init MoE is chaotic at bf16 precision: a flipped expert on a PROMPT token
+  changes that token's keys and values for every later query, an ulp in the rope table is enough to move a trajectory,
+  and at x16 only 4 of 21 qualified seeds reproduce the fp32 tokens.  The fixture uses a seed that every variant
+  reproduces (x8: the first three qualified seeds all do; seed 33 has the most distinct tokens), i.e. one whose
+  decisions have real margins; tests/test_pr1_gpu.py additionally checks arbitrary seeds against the routing-aligned
+  oracle, which holds for any seed.  The chosen seed, the tokens and the observed margins are recorded in
+  tests/golden/pr1_l4.npz.
 """
 from __future__ import annotations
 
@@ -40,7 +41,7 @@ PROMPT_LEN = 128
 NEW_TOKENS = 32
 WEIGHT_SEED = 0
 HEAD_GAIN_SIGMA = 2.5
-GATE_SCALE = 16.0
+GATE_SCALE = 8.0
 
 
 def config() -> VitaConfig:

@@ -17,12 +17,14 @@ from vita_b200.config import VitaConfig            # noqa: E402
 from vita_b200.model.mixtral import MixtralDecoder  # noqa: E402
 
 BASE = {"pdl": 1, "attn_early": 1, "attn_tagged": 1, "chain_wait": 1, "tc_prefetch_consts": 1, "tc_l2_ahead": 0,
-        "tc_trigger_lead": 0, "tc_wide_route": 1, "smem_carveout_max": 0, "chain_counters": 0}
+        "tc_trigger_lead": 0, "tc_wide_route": 1, "smem_carveout_max": 0, "chain_counters": 0, "tc_park": 1}
 CONFIGS = {
     # name: (library options on top of BASE, decoder attributes)
     "nopdl": ({"pdl": 0}, {}),
     "default": ({}, {}),
     "counters_on": ({"chain_counters": 1}, {}),
+    "park_off": ({"tc_park": 0}, {}),
+    "early_route_on": ({}, {"early_route": True}),
     "early_route_off": ({}, {"early_route": False}),
     "early_route_lead4": ({"tc_trigger_lead": 4}, {}),
     "carveout_default": ({"smem_carveout_max": 0}, {}),
@@ -54,7 +56,7 @@ def main():
         for n in names:
             opts, attrs = CONFIGS[n]
             opts = {**BASE, **opts}
-            attrs = {"decode_splits": 16, "early_route": True, **attrs}
+            attrs = {"decode_splits": 16, "early_route": False, **attrs}
             for k, v in opts.items():
                 ops.set_option(k, v)
             for k, v in attrs.items():

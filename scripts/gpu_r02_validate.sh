@@ -23,7 +23,7 @@ PY
 tail -3 gpurun_out/bench_r02.err | cut -c1-300
 python scripts/gemm_bench.py > gpurun_out/gemm_shapes.txt 2>&1; cut -c1-900 gpurun_out/gemm_shapes.txt | tee -a $S
 for a in "mix 4096" "mix 512" "vit 1025" "whale 248"; do timeout 200 python scripts/fa_check.py $a bench 2>&1 | grep fa_ | tee -a $S; done
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 4000 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 3 --layers 4 --new-tokens 4 --no-cpu-baseline --no-parity --no-long-prefill > gpurun_out/ncu_launches.log 2>&1
 echo "== ncu launches exit $?" | tee -a $S
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:TcGateUpOp -s 8 -c 1 \

@@ -112,3 +112,103 @@ def test_moe_grouped_small():
 
 def test_moe_grouped_full_width():
     _moe_case(4096, 14336, 8, [130, 90, 128, 0, 260, 64, 127, 225])
+
+
+@pytest.mark.parametrize("M,K,n_q,n_kv", [(37, 256, 4, 1), (506, 4096, 32, 8), (300, 512, 3, 2), (4096, 512, 32, 8)])
+def test_qkv_gemm_with_rope_and_kv_append_epilogue(M, K, n_q, n_kv):
+    """vita_gemm_qkv_rope == vita_gemm_bf16 followed by vita_rope_kv_write, bit for bit (qkv rows and both caches)."""
+    from vita_b200 import ops, weights
+    D = 128
+    N = (n_q + 2 * n_kv) * D
+    x, w = to_dev(randn((M, K), 1, 1.0)), to_dev(randn((N, K), 2, 0.05))
+    pos = (torch.arange(M, dtype=torch.int32) * 3 % 1000 + 5).cuda()
+    page, n_slots = 16, (M + 15) // 16 * 16
+    perm = torch.randperm(n_slots // page, generator=torch.Generator().manual_seed(0))
+    slots = torch.tensor([int(perm[p // page]) * page + p % page for p in range(M)], dtype=torch.int32).cuda()
+    table = weights.rope_table(1024, D, 1e6).cuda()
+    kc1 = torch.zeros(n_slots, n_kv, D, dtype=torch.bfloat16, device="cuda"); vc1 = torch.zeros_like(kc1)
+    kc2, vc2 = torch.zeros_like(kc1), torch.zeros_like(kc1)
+    two = ops.linear(x, w)
+    ops.rope_kv_write(two, pos, slots, table, kc1, vc1, n_q, n_kv, D)
+    one = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.linear_qkv_rope(x, w, one, pos, slots, table, kc2, vc2, n_q, n_kv, D)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+    # no cache write
+    three = torch.empty_like(one)
+    ops.linear_qkv_rope(x, w, three, pos, None, table, None, None, n_q, n_kv, D)
+    assert torch.equal(three, one)
+
+
+@pytest.mark.parametrize("T,H,I", [(301, 512, 1024), (1000, 4096, 14336), (16, 4096, 14336)])
+def test_fused_router_permute_slot_layout_equals_align_gather_flow(T, H, I):
+    """vita_moe_route_scatter + the *_slots grouped GEMMs + combine == router + align + gather + grouped GEMMs + combine,
+    bit for bit (the slot layout only moves rows)."""
+    from vita_b200 import ops
+    E = 8
+    dev = "cuda"
+    h0 = to_dev(randn((T, H), 1, 1.5))
+    nw, gw = to_dev(randn((H,), 2)), to_dev(randn((E, H), 3, 0.05))
+    g = torch.Generator(device=dev).manual_seed(4)
+    w13 = (torch.randn(E, 2 * I, H, device=dev, generator=g) * 0.03).to(torch.bfloat16)
+    w2 = (torch.randn(E, H, I, device=dev, generator=g) * 0.03).to(torch.bfloat16)
+    nxt = to_dev(randn((H,), 5))
+    i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+    bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)
+    # (a) align + gather flow
+    ha = h0.clone()
+    xn, ids, tw = bf(T, H), i32(T, 2), torch.empty(T, 2, device=dev)
+    ops.moe_router(ha, nw, gw, xn, ids, tw, 1e-5)
+    offs, perm, rtok, rw = i32(E + 1), i32(2 * T), i32(2 * T), torch.empty(2 * T, device=dev)
+    ops.moe_align(ids, tw, offs, perm, rtok, rw, T, E)
+    xp, act, yp = bf(2 * T, H), bf(2 * T, I), bf(2 * T, H)
+    ops.row_copy(xn, rtok, None, xp, 2 * T)
+    ops.moe_gate_up(xp, w13, act, offs, 2 * T)
+    ops.moe_down(act, w2, yp, offs, rw, 2 * T)
+    xa = bf(T, H)
+    ops.moe_combine(ha, yp, perm, nxt, xa, 1e-5)
+    # (b) fused router + permute over slots (capacity > T, buffers poisoned with NaN)
+    cap = T + 5
+    hb = h0.clone()
+    nanbf = lambda *s: torch.full(s, float("nan"), dtype=torch.bfloat16, device=dev)
+    xs, acts, ys = nanbf(E * cap, H), nanbf(E * cap, I), nanbf(E * cap, H)
+    cnt, perm2, rws = torch.zeros(E, dtype=torch.int32, device=dev), i32(2 * T), torch.empty(E * cap, device=dev)
+    ids2, tw2 = i32(T, 2), torch.empty(T, 2, device=dev)
+    ops.moe_route_scatter(hb, nw, gw, xs, cnt, perm2, rws, 1e-5, ids2, tw2)
+    assert torch.equal(ids2, ids) and torch.equal(tw2, tw)
+    assert cnt.cpu().tolist() == torch.bincount(ids.cpu().reshape(-1).long(), minlength=E).tolist()
+    p2 = perm2.view(T, 2).long()
+    assert torch.equal(p2 // cap, ids.long())                                  # every row sits in its expert's range
+    assert p2.reshape(-1).unique().numel() == 2 * T                            # and no row is claimed twice
+    assert torch.equal(xs[p2[:, 0]], xn) and torch.equal(xs[p2[:, 1]], xn)
+    assert torch.equal(rws[p2.reshape(-1)].view(T, 2), tw)
+    ops.moe_gate_up_slots(xs, w13, acts, cnt, 2 * T)
+    ops.moe_down_slots(acts, w2, ys, cnt, rws, 2 * T)
+    xb = bf(T, H)
+    ops.moe_combine(hb, ys, perm2, nxt, xb, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(ha, hb) and torch.equal(xa, xb)
+
+
+def test_moe_grouped_two_row_tiles_per_pass_keeps_the_bits(monkeypatch):
+    """MT = 2 (two 128-row tiles share every weight stage; gemm_sm100.cu) against one row tile per pass."""
+    from vita_b200 import ops
+    H, I, E = 1024, 2048, 8
+    counts = [130, 90, 256, 0, 257, 64, 127, 1]
+    rows = sum(counts)
+    offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32).cuda()
+    x = to_dev(randn((rows, H), 1, 1.0))
+    w13, w2 = to_dev(randn((E, 2 * I, H), 2, 0.05)), to_dev(randn((E, H, I), 3, 0.05))
+    rw = torch.rand(rows, generator=torch.Generator().manual_seed(4)).cuda()
+    outs = []
+    for mt in ("1", "2"):
+        monkeypatch.setenv("VITA_B200_GEMM_MT", mt)
+        act = torch.full((rows, I), float("nan"), dtype=torch.bfloat16, device="cuda")
+        y = torch.full((rows, H), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops.moe_gate_up(x, w13, act, offs, rows)
+        ops.moe_down(act, w2, y, offs, rw, rows)
+        torch.cuda.synchronize()
+        outs.append((act, y))
+    assert torch.isfinite(outs[1][0].float()).all() and torch.isfinite(outs[1][1].float()).all()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

@@ -28,6 +28,7 @@ SIGNATURES = {
     "vita_layernorm": (c_int, [P, P, P, P, I64, I64, c_float, c_int, c_float, P]),
     "vita_row_copy": (c_int, [P, P, P, P, I64, I64, P]),
     "vita_rope_kv_write": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
+    "vita_gemm_qkv_rope": (c_int, [P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P]),
     "vita_attention_fwd": (c_int, [P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P, c_int, I64, c_float, P]),
     "vita_decode_attention_workspace_bytes": (I64, [I64, I64, I64]),
     "vita_decode_attention": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, c_float, I64, P]),
@@ -43,6 +44,9 @@ SIGNATURES = {
     "vita_moe_gemm_gate_up_silu": (c_int, [P, P, P, P, I64, I64, I64, I64, P]),
     "vita_moe_gemm_down": (c_int, [P, P, P, P, P, I64, I64, I64, I64, P]),
     "vita_moe_combine": (c_int, [P, P, P, P, P, I64, I64, c_float, P]),
+    "vita_moe_route_scatter": (c_int, [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
+    "vita_moe_gemm_gate_up_silu_slots": (c_int, [P, P, P, P, I64, I64, I64, I64, I64, P]),
+    "vita_moe_gemm_down_slots": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, P]),
     "vita_add_rmsnorm": (c_int, [P, P, P, P, I64, I64, c_float, P]),
     "vita_vit_im2col": (c_int, [P, P, I64, I64, I64, I64, I64, P]),
     "vita_vit_assemble": (c_int, [P, P, P, P, I64, I64, I64, P]),

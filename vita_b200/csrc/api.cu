@@ -62,6 +62,9 @@ static Option g_options[] = {
     {"tc_wide_route", "VITA_B200_TC_WIDE_ROUTE", 1, {-1}},
     // tcgen05 decode kernels: weight tiles still to be issued by a CTA when it triggers the dependent launch
     {"tc_trigger_lead", "VITA_B200_TC_TRIGGER_LEAD", 0, {-1}},
+    // tcgen05 decode kernels: producer / MMA / x-writer threads that cannot proceed before the predecessor has completed
+    // wait in hardware (griddepcontrol.wait) instead of spinning on their mbarriers next to the predecessor's threads
+    {"tc_park", "VITA_B200_TC_PARK", 1, {-1}},
     // tcgen05 decode kernels: pull norm / router weights into L2 ahead of the dependency wait
     {"tc_prefetch_consts", "VITA_B200_TC_PREFETCH_CONSTS", 1, {-1}},
     // decode chain: per-kernel completion counters polled by the successor instead of griddepcontrol.wait

@@ -342,7 +342,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
                 // ring full for the first time: nothing can drain it before the predecessor has completed (the
                 // activations come from it), so park on the hardware dependency instead of spinning on the barrier
                 // next to the predecessor's own producer / MMA threads
-                if (u - u0 == STAGES) chain_wait(chain);
+                if ((flags & 4) && u - u0 == STAGES) chain_wait(chain);
                 mbar_wait(&empty_bar[stage], phase ^ 1, 22);
                 mbar_arrive_expect_tx(&full_bar[stage], STAGE_A);
 #pragma unroll
@@ -374,7 +374,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             long long u = u0;
-            chain_wait(chain);   // the activation vector derives from the predecessor: wait in hardware, not on full_bar
+            if (flags & 4) chain_wait(chain);   // the activation vector derives from the predecessor: wait in hardware, not on full_bar
             while (u < u1) {
                 const int rb = static_cast<int>(u / n_kb);
                 long long seg_end = static_cast<long long>(rb + 1) * n_kb;
@@ -440,7 +440,7 @@ tc_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Op op, unsigned lo
                 }
             }
         } else {
-            if (lane == 0) chain_wait(chain);
+            if ((flags & 4) && lane == 0) chain_wait(chain);
             __syncwarp();
             mbar_wait(x_ready, 0, 25);
             for (long long u = u0; u < u1; ++u) {
@@ -928,7 +928,7 @@ static int launch_tc(const Op& op, const void* W, long long w_rows, int K, int n
     dim3 grid(static_cast<unsigned>(g), B);
     const int l2_ahead = option("tc_l2_ahead");   // tiles per CTA prefetched into L2 behind the ring
     const int flags = (option("tc_prefetch_consts") ? 1 : 0) | (option("chain_wait") ? 2 : 0) |
-                      (option("tc_wide_route") ? 8 : 0) |
+                      (option("tc_wide_route") ? 8 : 0) | (option("tc_park") ? 4 : 0) |
                       (option("tc_trigger_lead") << 8);
     ChainArgsDev chain{nullptr, nullptr, nullptr, 0};
     if (B == 1) {   // the counters protocol covers the bs = 1 step (fixed grids per chain position)

@@ -174,8 +174,10 @@ rope_kv_write_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ po
         __nv_bfloat16* h = row + head * D;
         const float x1 = __bfloat162float(h[j]), x2 = __bfloat162float(h[j + HALF]);
         const float c = cs[j], s = cs[HALF + j];
-        const __nv_bfloat16 o1 = __float2bfloat16(x1 * c - x2 * s);
-        const __nv_bfloat16 o2 = __float2bfloat16(x2 * c + x1 * s);
+        float r1, r2;
+        rope_rotate(x1, x2, c, s, r1, r2);
+        const __nv_bfloat16 o1 = __float2bfloat16(r1);
+        const __nv_bfloat16 o2 = __float2bfloat16(r2);
         h[j] = o1;
         h[j + HALF] = o2;
         if (head >= n_q && slot >= 0) {
@@ -280,6 +282,118 @@ rmsnorm_router_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* 
         topk_ids[tok * 2 + 1] = i1;
         topk_w[tok * 2] = p0 / den;
         topk_w[tok * 2 + 1] = p1 / den;
+    }
+}
+
+// The same router with the token permute fused in ("fused top-2 router + token permute/scatter"): every expert owns
+// `capacity` consecutive rows of x_slots; the CTA of a token claims one row in each of its two experts (atomicAdd on the
+// expert's counter) and stores the normed activations there directly -- no offsets pass, no gather pass.  The order of the
+// rows inside an expert depends on the arrival order of the CTAs; every row is processed independently by the grouped
+// GEMMs, so the results do not.  perm_row[t, k] = the claimed row (what vita_moe_combine gathers by).
+template <int E>
+__global__ void __launch_bounds__(128)
+rmsnorm_router_scatter_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ norm_w,
+                              const __nv_bfloat16* __restrict__ gate_w, __nv_bfloat16* __restrict__ x_slots,
+                              int* __restrict__ expert_counts, int* __restrict__ perm_row,
+                              float* __restrict__ row_weight, int* __restrict__ topk_ids, float* __restrict__ topk_w,
+                              int n_tok, int H, int capacity, float eps) {
+    constexpr int MAXV = 4;
+    __shared__ float red[4][E + 1];
+    __shared__ int dst[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tok = blockIdx.x;
+    const uint4* hr = reinterpret_cast<const uint4*>(h + static_cast<long long>(tok) * H);
+    const int nvec = H >> 3;
+    uint4 hv[MAXV];
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = threadIdx.x + j * 128;
+        if (i < nvec) {
+            hv[j] = hr[i];
+            float f[8];
+            unpack8(hv[j], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ss += f[q] * f[q];
+        }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp][E] = ss;
+    __syncthreads();
+    const float inv = rsqrtf((red[0][E] + red[1][E] + red[2][E] + red[3][E]) / static_cast<float>(H) + eps);
+    float logit[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) logit[e] = 0.0f;
+    const uint4* nw = reinterpret_cast<const uint4*>(norm_w);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = threadIdx.x + j * 128;
+        if (i < nvec) {
+            float f[8], g[8];
+            unpack8(hv[j], f);
+            unpack8(__ldg(nw + i), g);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = f[q] * inv * g[q];
+            hv[j] = pack8(f);      // the normed row stays in registers until its two destinations are known
+            unpack8(hv[j], f);     // router sees the bf16-rounded activations
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                float wv[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(gate_w + static_cast<long long>(e) * H) + i), wv);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) logit[e] += f[q] * wv[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        logit[e] = warp_sum(logit[e]);
+        if (lane == 0) red[warp][e] = logit[e];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            logit[e] = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+            m = fmaxf(m, logit[e]);
+        }
+        float p[E], sum = 0.0f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { p[e] = expf(logit[e] - m); sum += p[e]; }
+        int i0 = 0;
+#pragma unroll
+        for (int e = 1; e < E; ++e) if (p[e] > p[i0]) i0 = e;
+        int i1 = (i0 == 0) ? 1 : 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) if (e != i0 && p[e] > p[i1]) i1 = e;
+        const float p0 = p[i0] / sum, p1 = p[i1] / sum;
+        const float den = p0 + p1;
+        const int r0 = i0 * capacity + atomicAdd(&expert_counts[i0], 1);
+        const int r1 = i1 * capacity + atomicAdd(&expert_counts[i1], 1);
+        dst[0] = r0;
+        dst[1] = r1;
+        perm_row[tok * 2] = r0;
+        perm_row[tok * 2 + 1] = r1;
+        row_weight[r0] = p0 / den;
+        row_weight[r1] = p1 / den;
+        if (topk_ids) {
+            topk_ids[tok * 2] = i0;
+            topk_ids[tok * 2 + 1] = i1;
+            topk_w[tok * 2] = p0 / den;
+            topk_w[tok * 2 + 1] = p1 / den;
+        }
+    }
+    __syncthreads();
+    uint4* x0 = reinterpret_cast<uint4*>(x_slots + static_cast<long long>(dst[0]) * H);
+    uint4* x1 = reinterpret_cast<uint4*>(x_slots + static_cast<long long>(dst[1]) * H);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = threadIdx.x + j * 128;
+        if (i < nvec) {
+            x0[i] = hv[j];
+            x1[i] = hv[j];
+        }
     }
 }
 
@@ -845,6 +959,21 @@ extern "C" int vita_moe_router(const void* h, const void* norm_w, const void* ga
     rmsnorm_router_kernel<8><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         BF(h), BF(norm_w), BF(gate_w), BFM(xn), topk_ids, topk_w, (int)n_tok, (int)H, eps);
     return check_launch("moe_router");
+}
+
+extern "C" int vita_moe_route_scatter(const void* h, const void* norm_w, const void* gate_w, void* x_slots,
+                                      int32_t* expert_counts, int32_t* perm_row, float* row_weight, int32_t* topk_ids,
+                                      float* topk_w, int64_t n_tok, int64_t H, int64_t E, int64_t capacity, float eps,
+                                      void* stream) {
+    VITA_REQUIRE(E == 8, "router is specialised for 8 experts (Mixtral-8x7B)");
+    VITA_REQUIRE(H % 8 == 0 && H <= 4096, "H must be a multiple of 8 and <= 4096");
+    VITA_REQUIRE(capacity >= n_tok, "an expert can receive every token: capacity must be >= n_tok");
+    VITA_REQUIRE((topk_ids == nullptr) == (topk_w == nullptr), "topk_ids and topk_w go together");
+    if (n_tok == 0) return VITA_OK;
+    rmsnorm_router_scatter_kernel<8><<<static_cast<unsigned>(n_tok), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        BF(h), BF(norm_w), BF(gate_w), BFM(x_slots), expert_counts, perm_row, row_weight, topk_ids, topk_w, (int)n_tok,
+        (int)H, (int)capacity, eps);
+    return check_launch("moe_route_scatter");
 }
 
 extern "C" int vita_moe_align(const int32_t* topk_ids, const float* topk_w, int32_t* expert_offsets,

@@ -302,6 +302,12 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
     p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xr.y) << 23));
     return p;
 }
+// rotate-half RoPE of one (x[j], x[j + D/2]) pair (transformers apply_rotary_pos_emb, modeling_mixtral.py:232-254).  One
+// definition for the stand-alone pass and the qkv GEMM epilogue, so both round identically.
+__device__ __forceinline__ void rope_rotate(float x1, float x2, float c, float s, float& o1, float& o2) {
+    o1 = x1 * c - x2 * s;
+    o2 = x2 * c + x1 * s;
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 

@@ -115,9 +115,12 @@ class MixtralDecoder:
         # vita_mixtral.py:108,185-190): set to a list to have prefill() and the eager decode step append one
         # (top-2 ids [T, 2] int32, renormalised weights [T, 2] fp32) pair per layer
         self.route_trace: Optional[list] = None
-        # decode: the gate|up kernel publishes the expert pair as soon as its router is done and the down projection
-        # streams its weight rows while gate|up is still running (VITA_B200_EARLY_ROUTE=0 switches the hand-over off)
-        self.early_route = os.environ.get("VITA_B200_EARLY_ROUTE", "1") == "1"
+        # decode: the gate|up kernel can publish the expert pair as soon as its router is done so that the down projection
+        # streams its weight rows while gate|up is still running.  Bit-identical, but two same-box A/Bs measured it 0.7 %
+        # SLOWER (5.12 vs 5.08 and 5.27 vs 5.23 ms/token, profiles/r02_decode_ab.txt): off unless VITA_B200_EARLY_ROUTE=1
+        self.early_route = os.environ.get("VITA_B200_EARLY_ROUTE", "0") == "1"
+        # prefill / batched decode: fused top-2 router + token permute over per-expert slot ranges (0 = align + gather)
+        self.moe_fused = os.environ.get("VITA_B200_MOE_FUSED", "1") == "1"
         per = cfg.num_local_experts // self.ep_world
         self.e_lo, self.e_hi = self.ep_rank * per, (self.ep_rank + 1) * per
         assert weights["layers"][0]["w13"].shape[0] == per, "expert tensors do not match the EP layout"
@@ -216,11 +219,17 @@ class MixtralDecoder:
     def _alloc_ws(self, cap, H, I, E, dev):
         c = self.cfg
         e = lambda *shape, dt=BF16: torch.empty(*shape, dtype=dt, device=dev)
+        # MoE activations in the "slot" layout of the fused router + permute: expert e owns rows [e * cap, (e + 1) * cap)
+        # (any expert may receive every token).  The compact buffers of the align / gather flow (expert parallelism, the
+        # vLLM-shaped adapter) are the first 2 * cap rows of the same storage.
+        xs, acts, ys, rws = e(E * cap, H), e(E * cap, I), e(E * cap, H), e(E * cap, dt=torch.float32)
         return dict(
             cap=cap, xn=e(cap, H), qkv=e(cap, c.qkv_rows), attn=e(cap, c.num_attention_heads * c.head_dim),
             xn2=e(cap, H), ids=e(cap, 2, dt=torch.int32), tw=e(cap, 2, dt=torch.float32),
             offs=e(E + 1, dt=torch.int32), perm=e(cap * 2, dt=torch.int32), rtok=e(cap * 2, dt=torch.int32),
-            rw=e(cap * 2, dt=torch.float32), xp=e(cap * 2, H), act=e(cap * 2, I), yp=e(cap * 2, H),
+            xs=xs, acts=acts, ys=ys, rws=rws,
+            cnt=torch.zeros(c.num_hidden_layers, E, dtype=torch.int32, device=dev),
+            rw=rws[:cap * 2], xp=xs[:cap * 2], act=acts[:cap * 2], yp=ys[:cap * 2],
             ybuf=e(cap, H) if self.ep_world > 1 else None, rassign=e(cap * 2, dt=torch.int32),
             pos=torch.arange(cap, dtype=torch.int32, device=dev))
 
@@ -255,19 +264,32 @@ class MixtralDecoder:
         slots = self.cache.slot_map[slot, :S]
         W = c.qkv_rows
         layers = w["layers"]
+        fused = self.ep_world == 1 and self.moe_fused
+        if fused:
+            ws["cnt"].zero_()          # per-layer expert counters of the fused router + permute
         ops.rmsnorm(h, layers[0]["ln1"], c.rms_norm_eps, out=xn)
         for li, lw in enumerate(layers):
-            ops.linear(xn, lw["wqkv"], out=qkv)
-            ops.rope_kv_write(qkv, pos, slots, w["rope"], self.cache.k[li], self.cache.v[li], nq, nkv, D)
+            # qkv projection, RoPE and the KV append in one kernel (GEMM epilogue)
+            ops.linear_qkv_rope(xn, lw["wqkv"], qkv, pos, slots, w["rope"], self.cache.k[li], self.cache.v[li], nq, nkv, D)
             ops.attention(qkv, qkv[:, nq * D:], qkv[:, (nq + nkv) * D:], attn, (0, W, D), (0, W, D), (0, W, D),
                           (0, nq * D, D), 1, nq, nkv, S, S, D, D, None, True, D ** -0.5)
             ops.linear(attn, lw["wo"], residual=h, out=h)
+            nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else (w["norm"] if all_logits else None)
+            if fused:
+                # router + permute in one kernel (slot layout), grouped GEMMs over the slots, gather-combine
+                cnt = ws["cnt"][li]
+                ops.moe_route_scatter(h, lw["ln2"], lw["gate"], ws["xs"], cnt, perm, ws["rws"], c.rms_norm_eps, ids, tw)
+                if self.route_trace is not None:
+                    self.route_trace.append((ids.clone(), tw.clone()))
+                ops.moe_gate_up_slots(ws["xs"], lw["w13"], ws["acts"], cnt, 2 * S)
+                ops.moe_down_slots(ws["acts"], lw["w2"], ws["ys"], cnt, ws["rws"], 2 * S)
+                ops.moe_combine(h, ws["ys"], perm, nxt, xn if nxt is not None else None, c.rms_norm_eps)
+                continue
             ops.moe_router(h, lw["ln2"], lw["gate"], xn2, ids, tw, c.rms_norm_eps)
             if self.route_trace is not None:
                 self.route_trace.append((ids.clone(), tw.clone()))
             ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, S, E, row_assign=ws["rassign"][:2 * S])
             ops.row_copy(xn2, rtok, None, xp, 2 * S)
-            nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else (w["norm"] if all_logits else None)
             if p2p is not None:
                 # fused expert-parallel combine over NVLink peer memory: the down-projection epilogue pushes every
                 # (token, k) row to the token's owner; owners reduce + norm + all-gather by P2P stores
@@ -349,8 +371,8 @@ class MixtralDecoder:
             sy["epoch"] += 1
             ep = sy["epoch"]
             if n:
-                ops.linear(xn_own, lw["wqkv"], out=qkv)
-                ops.rope_kv_write(qkv, pos, slots, w["rope"], self.cache.k[li], self.cache.v[li], nq, nkv, D)
+                ops.linear_qkv_rope(xn_own, lw["wqkv"], qkv, pos, slots, w["rope"], self.cache.k[li],
+                                    self.cache.v[li], nq, nkv, D)
                 ko = off["kv"] + 2 * li * kvl + t0 * kvr
                 ops.ep_push(sy["base_ptrs"], [(ko, n * kvr), (ko + kvl, n * kvr)], N, r)
             ops.ep_signal(sy["flag_ptrs"], 2, N, r, ep)
@@ -494,27 +516,36 @@ class MixtralDecoder:
         perm, rtok, rw = ws["perm"][:2 * B], ws["rtok"][:2 * B], ws["rw"][:2 * B]
         xp, act, yp = ws["xp"][:2 * B], ws["act"][:2 * B], ws["yp"][:2 * B]
         layers = w["layers"]
+        if self.moe_fused:
+            ws["cnt"].zero_()
         ops.rmsnorm(h, layers[0]["ln1"], c.rms_norm_eps, out=xn)
         for li, lw in enumerate(layers):
-            ops.linear(xn, lw["wqkv"], out=qkv)
-            ops.rope_kv_write(qkv, cache.cur_pos[:B], slots, w["rope"], cache.k[li], cache.v[li], nq, nkv, D)
+            ops.linear_qkv_rope(xn, lw["wqkv"], qkv, cache.cur_pos[:B], slots, w["rope"], cache.k[li], cache.v[li],
+                                nq, nkv, D)
             ops.decode_attention(qkv, cache.k[li], cache.v[li], cache.block_table[:B], cache.cur_pos[:B], attn,
                                  self.attn_ws, nq, nkv, D, cache.page_size, self.decode_splits, D ** -0.5,
                                  q_stride=c.qkv_rows)
             ops.linear(attn, lw["wo"], residual=h, out=h)
+            nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else w["norm"]
+            if self.moe_fused:
+                cnt = ws["cnt"][li]
+                ops.moe_route_scatter(h, lw["ln2"], lw["gate"], ws["xs"], cnt, perm, ws["rws"], c.rms_norm_eps)
+                ops.moe_gate_up_slots(ws["xs"], lw["w13"], ws["acts"], cnt, 2 * B)
+                ops.moe_down_slots(ws["acts"], lw["w2"], ws["ys"], cnt, ws["rws"], 2 * B)
+                ops.moe_combine(h, ws["ys"], perm, nxt, xn, c.rms_norm_eps)
+                continue
             ops.moe_router(h, lw["ln2"], lw["gate"], xn2, ids, tw, c.rms_norm_eps)
             ops.moe_align(ids, tw, ws["offs"], perm, rtok, rw, B, E)
             ops.row_copy(xn2, rtok, None, xp, 2 * B)
             ops.moe_gate_up(xp, lw["w13"], act, ws["offs"], 2 * B)
             ops.moe_down(act, lw["w2"], yp, ws["offs"], rw, 2 * B)
-            nxt = layers[li + 1]["ln1"] if li + 1 < len(layers) else w["norm"]
             ops.moe_combine(h, yp, perm, nxt, xn, c.rms_norm_eps)
         logits = ops.linear(xn, w["lm_head"], out=self.d_logits[:B])
         ops.argmax_rows(logits, self.best[:B])
 
     @property
     def launches_per_batched_step(self) -> int:
-        return 5 + 11 * self.cfg.num_hidden_layers
+        return (6 + 8 * self.cfg.num_hidden_layers) if self.moe_fused else (5 + 10 * self.cfg.num_hidden_layers)
 
     @torch.no_grad()
     def decode_step_batched(self, B: int, use_graph: bool = True):

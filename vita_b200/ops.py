@@ -104,6 +104,24 @@ def rope_kv_write(qkv: torch.Tensor, positions: torch.Tensor, slot_mapping: Opti
               qkv.shape[0], n_q, n_kv, head_dim, _stream())
 
 
+def linear_qkv_rope(x: torch.Tensor, w_qkv: torch.Tensor, out: torch.Tensor, positions: torch.Tensor,
+                    slot_mapping: Optional[torch.Tensor], cos_sin: torch.Tensor, k_cache: Optional[torch.Tensor],
+                    v_cache: Optional[torch.Tensor], n_q: int, n_kv: int, head_dim: int) -> torch.Tensor:
+    """qkv projection with RoPE + paged-KV append in the GEMM epilogue (== linear() then rope_kv_write(), one kernel)."""
+    _chk(x, BF16, "x", contiguous=False); _chk(w_qkv, BF16, "w_qkv"); _chk(out, BF16, "out")
+    _chk(positions, torch.int32, "positions"); _chk(cos_sin, torch.float32, "cos_sin")
+    M, K = x.shape
+    if x.stride(1) != 1 or w_qkv.shape != ((n_q + 2 * n_kv) * head_dim, K) or out.shape != (M, w_qkv.shape[0]):
+        raise _lib.VitaB200Error("linear_qkv_rope: shape mismatch")
+    if positions.numel() < M or (slot_mapping is not None and slot_mapping.numel() < M):
+        raise _lib.VitaB200Error("linear_qkv_rope: positions / slot_mapping shorter than the row count")
+    if slot_mapping is not None:
+        _chk(slot_mapping, torch.int32, "slot_mapping"); _chk(k_cache, BF16, "k_cache"); _chk(v_cache, BF16, "v_cache")
+    _lib.call("vita_gemm_qkv_rope", _p(x), x.stride(0), _p(w_qkv), _p(out), M, K, n_q, n_kv, head_dim, _p(positions),
+              _p(slot_mapping), _p(cos_sin), _p(k_cache), _p(v_cache), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def attention(q, k, v, out, q_strides, k_strides, v_strides, o_strides, B, n_q, n_kv, Sq, Skv, d_qk, d_v,
               kv_lens: Optional[torch.Tensor], causal: bool, scale: float, q_pos0: int = 0) -> torch.Tensor:
@@ -205,6 +223,34 @@ def moe_down(act, w_down, y_perm, expert_offsets, row_weight, rows):
     E, H, I = w_down.shape
     _lib.call("vita_moe_gemm_down", _p(act), _p(w_down), _p(y_perm), _p(expert_offsets), _p(row_weight), rows, E, H, I,
               _stream())
+
+
+def moe_route_scatter(h, norm_w, gate_w, x_slots, expert_counts, perm_row, row_weight, eps, topk_ids=None, topk_w=None):
+    """Fused router + permute: x_slots [E * capacity, H], expert_counts [E] (zero on entry)."""
+    _chk(h, BF16, "h"); _chk(norm_w, BF16, "norm_w"); _chk(gate_w, BF16, "gate_w"); _chk(x_slots, BF16, "x_slots")
+    _chk(expert_counts, torch.int32, "expert_counts"); _chk(perm_row, torch.int32, "perm_row")
+    _chk(row_weight, torch.float32, "row_weight")
+    n_tok, H = h.shape
+    E = gate_w.shape[0]
+    capacity = x_slots.shape[0] // E
+    if row_weight.numel() < E * capacity or perm_row.numel() < 2 * n_tok or expert_counts.numel() < E:
+        raise _lib.VitaB200Error("moe_route_scatter: output buffers too small")
+    _lib.call("vita_moe_route_scatter", _p(h), _p(norm_w), _p(gate_w), _p(x_slots), _p(expert_counts), _p(perm_row),
+              _p(row_weight), _p(topk_ids), _p(topk_w), n_tok, H, E, capacity, float(eps), _stream())
+
+
+def moe_gate_up_slots(x_slots, w_gate_up, act_slots, expert_counts, rows_hint):
+    _chk(x_slots, BF16, "x_slots"); _chk(w_gate_up, BF16, "w_gate_up"); _chk(act_slots, BF16, "act_slots")
+    E, two_i, H = w_gate_up.shape
+    _lib.call("vita_moe_gemm_gate_up_silu_slots", _p(x_slots), _p(w_gate_up), _p(act_slots), _p(expert_counts),
+              x_slots.shape[0] // E, rows_hint, E, H, two_i // 2, _stream())
+
+
+def moe_down_slots(act_slots, w_down, y_slots, expert_counts, row_weight, rows_hint):
+    _chk(act_slots, BF16, "act_slots"); _chk(w_down, BF16, "w_down"); _chk(y_slots, BF16, "y_slots")
+    E, H, I = w_down.shape
+    _lib.call("vita_moe_gemm_down_slots", _p(act_slots), _p(w_down), _p(y_slots), _p(expert_counts), _p(row_weight),
+              act_slots.shape[0] // E, rows_hint, E, H, I, _stream())
 
 
 def moe_combine(h, y_perm, perm_row, next_norm_w, xn_out, eps):

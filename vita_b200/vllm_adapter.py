@@ -203,8 +203,7 @@ class MixtralForConditionalGeneration:
         for li, lw in enumerate(layers):
             kc = kv_caches[li][0].reshape(-1, nkv, D)       # engine-owned pages, vLLM flash layout
             vc = kv_caches[li][1].reshape(-1, nkv, D)
-            ops.linear(xn, lw["wqkv"], out=qkv)
-            ops.rope_kv_write(qkv, positions, slots, w["rope"], kc, vc, nq, nkv, D)
+            ops.linear_qkv_rope(xn, lw["wqkv"], qkv, positions, slots, w["rope"], kc, vc, nq, nkv, D)
             for r0, n in prefills:
                 q = qkv[r0:r0 + n]
                 ops.attention(q, q[:, nq * D:], q[:, (nq + nkv) * D:], attn[r0:r0 + n], (0, W_, D), (0, W_, D),
