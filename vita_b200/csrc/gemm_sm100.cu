@@ -570,11 +570,13 @@ static int gemm_dispatch(const void* A, long long lda, int a_rows, const void* B
     }
     // two row tiles per pass for grouped GEMMs whose groups hold roughly 100-256 rows (S ~ 400-1000 prompt tokens over
     // 8 experts): the second row tile of a group reuses the weight stage instead of streaming it again
-    const char* mt_env = getenv("VITA_B200_GEMM_MT");   // tuning aid: 1 / 2 force the row-tile count
+    const char* mt_env = getenv("VITA_B200_GEMM_MT");   // 2 = use the two-row-tile variant for the grouped GEMMs
     const int rows_per_group = occ_rows / (args.num_groups > 0 ? args.num_groups : 1);
-    bool two_row_tiles = args.num_groups > 1 && block_n == 256 && rows_per_group > 96 && rows_per_group <= 256;
-    if (mt_env && atoi(mt_env) == 1) two_row_tiles = false;
-    if (mt_env && atoi(mt_env) == 2) two_row_tiles = block_n == 256;
+    // Measured (profiles/r02_gemm_shapes.txt, S = 506): 395 vs 338 us for gate|up, 204 vs 184 us for down -- the variant
+    // has one ring stage less (3 x 64 KB) and, with the whole TMEM holding its two accumulators, no epilogue overlap, which
+    // costs more HBM idle time than the second pass over an L2-resident weight tile it saves.  Opt-in only.
+    (void)rows_per_group;
+    const bool two_row_tiles = mt_env && atoi(mt_env) == 2 && block_n == 256 && args.num_groups > 1;
     if (two_row_tiles) {
         if (silu) return launch_gemm<256, true, 3, 2>(tmA, tmB, tmBs, a2, max_tiles, stream);
         return launch_gemm<256, false, 3, 2>(tmA, tmB, tmBs, a2, max_tiles, stream);
