@@ -77,3 +77,33 @@ def test_synthetic_weights_are_reproducible_and_bf16_exact():
         assert torch.equal(a[k], b[k]) and a[k].dtype == torch.bfloat16
     assert any(not torch.equal(a[k], c[k]) for k in a)
     assert set(W.all_param_shapes(cfg)) == set(W.synthetic_state(cfg, 0))
+
+
+def test_oracle_route_override_is_identity_on_its_own_decisions_and_reports_the_margins():
+    """`sparse_moe(route=...)` (the checker aid of tests/full_depth.py): given the oracle's own expert pairs it reproduces
+    the default path bit for bit; given another pair it evaluates those experts with the oracle's renormalised weights."""
+    import torch
+    from oracle import vita_oracle as O
+    from vita_b200.config import VitaConfig
+    from vita_b200 import weights as W
+    cfg = VitaConfig.tiny() if hasattr(VitaConfig, "tiny") else None
+    if cfg is None:
+        import pytest
+        pytest.skip("no tiny config")
+    state = W.synthetic_state(cfg, 3, parts=("llm",))
+    lc = cfg.llm
+    xn = torch.randn(11, lc.hidden_size, generator=torch.Generator().manual_seed(0))
+    y0, ids0, w0 = O.sparse_moe(state, lc, 0, xn)
+    route = {"ids": ids0.clone()}
+    y1, ids1, w1 = O.sparse_moe(state, lc, 0, xn, None, route)
+    assert torch.equal(y0, y1) and torch.equal(ids0, ids1) and torch.equal(w0, w1)
+    assert torch.equal(route["own_ids"], ids0) and route["logits"].shape == (11, lc.num_local_experts)
+    # swap the second expert of token 0 for another one: only that token's output changes, weights renormalise over the pair
+    other = next(e for e in range(lc.num_local_experts) if e not in ids0[0].tolist())
+    forced = ids0.clone()
+    forced[0, 1] = other
+    route = {"ids": forced}
+    y2, ids2, w2 = O.sparse_moe(state, lc, 0, xn, None, route)
+    assert torch.allclose(y2[1:], y0[1:], rtol=1e-5, atol=1e-6) and not torch.allclose(y2[0], y0[0], rtol=1e-3)
+    p = torch.softmax(route["logits"][0], -1)[forced[0]]
+    assert torch.allclose(w2[0], p / p.sum(), atol=1e-6)

@@ -71,7 +71,7 @@ class MixtralDecoder:
         #   p2p  replicated dense part, fused P2P combine (round-1 design, kept as the A/B baseline)
         #   nccl replicated dense part, partial sums + NCCL all-reduce (library baseline)
         self.ep_rank, self.ep_world = weights.get("ep", (0, 1))
-        self.ep_mode = os.environ.get("VITA_B200_EP", "p2p") if self.ep_world > 1 else None
+        self.ep_mode = os.environ.get("VITA_B200_EP", "seq") if self.ep_world > 1 else None
         assert self.ep_mode in (None, "seq", "p2p", "nccl"), "VITA_B200_EP must be seq, p2p or nccl"
         self.ep_p2p = None
         storage = None
@@ -158,9 +158,10 @@ class MixtralDecoder:
         self.ep_p2p = dict(
             sym=sym, hdl=hdl, chunk_max=chunk_max, off=off, kv_layer=kv_layer, kv_row=kv_row,
             base_ptrs=torch.tensor(bases, dtype=torch.int64, device=dev),
-            rs=view("rs", BF16), h=view("h", BF16).view(S_max, H), xn=view("xn", BF16).view(S_max, H),
-            xn2=view("xn2", BF16).view(S_max, H), ids=view("ids", torch.int32).view(S_max, 2),
-            tw=view("tw", torch.float32).view(S_max, 2), flags=view("flags", torch.int32),
+            rs=view("rs", BF16), h=view("h", BF16)[:S_max * H].view(S_max, H),
+            xn=view("xn", BF16)[:S_max * H].view(S_max, H), xn2=view("xn2", BF16)[:S_max * H].view(S_max, H),
+            ids=view("ids", torch.int32)[:S_max * 2].view(S_max, 2),      # (the regions are padded to 256 bytes)
+            tw=view("tw", torch.float32)[:S_max * 2].view(S_max, 2), flags=view("flags", torch.int32),
             rs_ptrs=ptrs("rs"), h_ptrs=ptrs("h"), xn_ptrs=ptrs("xn"), flag_ptrs=ptrs("flags"), epoch=0)
         dist.barrier()
 
@@ -199,7 +200,7 @@ class MixtralDecoder:
         ptrs = lambda i: torch.tensor([b + offs[i] for b in bases], dtype=torch.int64, device=dev)
         self.ep_p2p = dict(
             sym=sym, hdl=hdl, chunk_max=chunk_max,
-            rs=view(0, BF16), h=view(1, BF16).view(S_max, H), xn=view(2, BF16).view(S_max, H),
+            rs=view(0, BF16), h=view(1, BF16)[:S_max * H].view(S_max, H), xn=view(2, BF16)[:S_max * H].view(S_max, H),
             flags=view(3, torch.int32), rs_ptrs=ptrs(0), h_ptrs=ptrs(1), xn_ptrs=ptrs(2), flag_ptrs=ptrs(3), epoch=0)
         dist.barrier()
 
