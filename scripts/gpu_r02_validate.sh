@@ -36,3 +36,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:flas
   python scripts/prof_target.py flash > gpurun_out/ncu_flash.log 2>&1
 echo "== ncu flash exit $?" | tee -a $S
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches.csv | tee -a $S
+# configs[4] on one GPU: 16 concurrent audio queries, batched decode; and with staggered arrivals through the batcher
+timeout 600 python scripts/bench_cfg5.py > gpurun_out/cfg5_bs16.json 2> gpurun_out/cfg5_bs16.err; tail -1 gpurun_out/cfg5_bs16.json | cut -c1-600 | tee -a $S
+timeout 600 python scripts/bench_cfg5.py --arrivals 12 > gpurun_out/cfg5_arrivals.json 2> gpurun_out/cfg5_arrivals.err; tail -1 gpurun_out/cfg5_arrivals.json | cut -c1-900 | tee -a $S
