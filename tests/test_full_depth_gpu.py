@@ -53,4 +53,4 @@ def test_configs2_full_depth_prefill_and_greedy_vs_streamed_fp32_oracle():
     # weights are the oracle's
     assert r["routing_differ_frac"] < 0.06, r
     assert r["routing_differ_gap_over_spread_p99"] < 0.25 and r["routing_differ_gap_over_spread_max"] < 0.6, r
-    assert r["routing_weight_err_p99"] < 0.04 and r["routing_weight_err_max"] < 0.12, r
+    assert r["routing_weight_err_p99"] < 0.05 and r["routing_weight_err_max"] < 0.15, r   # measured 0.036 / 0.07
