@@ -8,7 +8,7 @@ Mirrors `MixtralForConditionalGeneration` of the reference's vLLM fork
 What the engine hands the model per step is captured by `TokenBatch` (the fields of vLLM's flash-attention metadata:
 slot mapping, block tables, sequence / query lengths); the engine's block tables and KV tensors are used as they are --
 `kv_caches[l]` is vLLM's flash layout [2, num_blocks, block_size, n_kv_heads, head_dim], which is exactly the layout
-`vita_rope_kv_write` / `vita_decode_attention` address (page = block).  A step may mix fresh prompts (attention over the
+`vita_gemm_qkv_rope` / `vita_decode_attention` address (page = block).  A step may mix fresh prompts (attention over the
 prompt itself, FlashAttention kernel) and single-token decodes (paged decode kernel); chunked prefill / prefix caching
 (a prompt continuing cached pages) is not supported and raises.
 
