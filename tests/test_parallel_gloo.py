@@ -178,6 +178,24 @@ def test_sequence_sharded_expert_parallel_layer_two_ranks():
     assert all(r[2] < 2e-5 for r in res), res
 
 
+def test_sequence_sharded_expert_parallel_layer_four_ranks():
+    """The same decomposition with 4 ranks and S = 37: chunks of 16 tokens, the last rank owns none (the case the
+    epoch-keeping branch of MixtralDecoder._prefill_ep_seq exists for) and every rank holds two experts."""
+    world, port = 4, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_seq_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ranges = [r[1] for r in res]
+    assert ranges[0][0] == 0 and ranges[-1][1] == 37 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert all(r[2] < 2e-5 for r in res), res
+
+
 def test_token_ranges_cover_the_sequence():
     from vita_b200 import parallel
     for S in (1, 7, 8, 37, 300, 4096, 4097):
